@@ -1,0 +1,375 @@
+// tcgen05 flash-attention forward for sm_100a (non-causal, no mask):  O = softmax(scale · Q Kᵀ) V
+//
+// One CTA owns 256 query rows of one (batch, head): two 128-row tiles ping-ponged through one tensor pipe.
+//   warp 0      TMA producer: Q tiles once, then a STAGES-deep ring of 64-key K/V tiles (strided 4-D tensor maps, so
+//               q/k/v are read in place from the fused QKV GEMM output)
+//   warp 1      MMA issuer (one lane):  S_i = Q_i·K_jᵀ   (SS, 128x64x16, K-major K tile)
+//                                       O_i += P_i·V_j   (SS, 128xDx16, MN-major V tile; P_i staged as bf16 in smem)
+//   warps 2-5   softmax warpgroup for tile 0;  warps 6-9: tile 1.   thread == query row (tcgen05.ld 32x32b), so the row
+//               max / row sum need no cross-thread traffic.  exp2 with the scale folded in; O is rescaled lazily (only
+//               when the running max grew by more than 2^8), which is exact after the final 1/rowsum normalisation.
+// TMEM: S0 [0,64) S1 [64,128) O0 [128,128+D) O1 [128+D,128+2D)  -> 512 columns allocated.
+// The issue order  S0 S1 | PV0 S0' PV1 S1' | ...  keeps the tensor pipe busy with tile 1 while warpgroup 0 is in softmax.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/actionmesh_b200.h"
+
+namespace amb {
+
+constexpr int ATT_BQ = 128;   // rows per query tile
+constexpr int ATT_BK = 64;    // keys per K/V tile
+constexpr int ATT_THREADS = 320;
+
+struct AttnParams {
+  __nv_bfloat16* o;
+  long long o_stride_b, o_stride_h, o_stride_s;
+  int heads, sq, sk;
+  int kv_chunks, sk_chunk;   // kv split into chunks along the outermost tensor-map coordinate
+  float scale_log2;          // scale * log2(e)
+};
+
+template <int D, int STAGES>
+struct AttnSmem {
+  static constexpr int Q_TILE_BYTES = ATT_BQ * D * 2;          // one query tile (D/64 column halves of 16 KB)
+  static constexpr int KV_TILE_BYTES = ATT_BK * D * 2;         // one K or V tile
+  static constexpr int P_TILE_BYTES = ATT_BQ * ATT_BK * 2;     // 16 KB
+  static constexpr int Q_OFF = 0;
+  static constexpr int P_OFF = 2 * Q_TILE_BYTES;
+  static constexpr int KV_OFF = P_OFF + 2 * P_TILE_BYTES;
+  static constexpr int BAR_OFF = KV_OFF + STAGES * 2 * KV_TILE_BYTES;
+  static constexpr int NUM_BARS = 1 + 2 * STAGES + 2 + 2 + 2;  // q_full, kv_full[], kv_empty[], s_full[2], p_ready[2], o_full[2]
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int D, int STAGES>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnSmem<D, STAGES>;
+  constexpr int DH = D / 64;  // 64-column halves per row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* kv_full = q_full + 1;
+  uint64_t* kv_empty = kv_full + STAGES;
+  uint64_t* s_full = kv_empty + STAGES;  // [2]
+  uint64_t* p_ready = s_full + 2;        // [2]
+  uint64_t* o_full = p_ready + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_kv = p.kv_chunks * ((p.sk_chunk + ATT_BK - 1) / ATT_BK);  // K/V tiles in total
+  const int tiles_per_chunk = (p.sk_chunk + ATT_BK - 1) / ATT_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&kv_full[s], 1);
+        mbar_init(&kv_empty[s], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_ready[i], 128);
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s[2] = {tmem_base, tmem_base + 64};
+  const uint32_t tmem_o[2] = {tmem_base + 128, tmem_base + 128 + D};
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, 2 * L::Q_TILE_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int c = 0; c < DH; ++c)
+          tma_load_4d(smem + L::Q_OFF + i * L::Q_TILE_BYTES + c * (ATT_BQ * 128), &tmQ, q_full, c * 64,
+                      q0 + i * ATT_BQ, head, batch, kEvictFirst);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int chunk = j / tiles_per_chunk;
+        const int key0 = (j - chunk * tiles_per_chunk) * ATT_BK;
+        mbar_wait(&kv_empty[s], phase ^ 1);
+        mbar_expect_tx(&kv_full[s], 2 * L::KV_TILE_BYTES);
+        uint8_t* sk = smem + L::KV_OFF + s * 2 * L::KV_TILE_BYTES;
+        uint8_t* sv = sk + L::KV_TILE_BYTES;
+        // tensor-map coordinate 3 = batch * kv_chunks + chunk  (chunks are an extra outer dimension)
+        const int c3 = batch * p.kv_chunks + chunk;
+        for (int c = 0; c < DH; ++c) {
+          tma_load_4d(sk + c * (ATT_BK * 128), &tmK, &kv_full[s], c * 64, key0, head, c3, kEvictLast);
+          tma_load_4d(sv + c * (ATT_BK * 128), &tmV, &kv_full[s], c * 64, key0, head, c3, kEvictLast);
+        }
+        if (++s == STAGES) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);  // S[128 x 64]  = Q (K-major) · K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);      // O[128 x D]  += P (K-major) · V (MN-major)
+      const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+      const uint32_t sp_addr = smem_u32(smem + L::P_OFF);
+      const uint32_t skv_addr = smem_u32(smem + L::KV_OFF);
+
+      auto issue_qk = [&](int i, int stage) {
+        const uint32_t qa = sq_addr + i * L::Q_TILE_BYTES;
+        const uint32_t ka = skv_addr + stage * 2 * L::KV_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t half = k >> 2, ko = (k & 3) * 32;
+          mma_ss(tmem_s[i], make_desc_kmajor_sw128(qa + half * (ATT_BQ * 128) + ko),
+                 make_desc_kmajor_sw128(ka + half * (ATT_BK * 128) + ko), idesc_qk, k != 0);
+        }
+        tc_commit(&s_full[i]);
+      };
+      auto issue_pv = [&](int i, int stage, bool accumulate) {
+        const uint32_t pa = sp_addr + i * L::P_TILE_BYTES;
+        const uint32_t va = skv_addr + stage * 2 * L::KV_TILE_BYTES + L::KV_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k) {
+          // V tile: [64 keys][64 d] boxes of 128-B rows; 16 keys = 2048 B; next 64 d-columns ATT_BK*128 B further
+          mma_ss(tmem_o[i], make_desc_kmajor_sw128(pa + k * 32),
+                 make_desc_mnmajor_sw128(va + k * 2048, ATT_BK * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        int s_next = s + 1;
+        uint32_t phase_next = phase;
+        if (s_next == STAGES) { s_next = 0; phase_next ^= 1; }
+        const bool has_next = (j + 1 < n_kv);
+        // ---- tile 0
+        mbar_wait(&p_ready[0], j & 1);
+        tc_fence_after();
+        issue_pv(0, s, j > 0);
+        if (has_next) {
+          mbar_wait(&kv_full[s_next], phase_next);
+          tc_fence_after();
+          issue_qk(0, s_next);
+        } else {
+          tc_commit(&o_full[0]);
+        }
+        // ---- tile 1
+        mbar_wait(&p_ready[1], j & 1);
+        tc_fence_after();
+        issue_pv(1, s, j > 0);
+        tc_commit(&kv_empty[s]);  // K_j and V_j fully consumed once everything issued so far has completed
+        if (has_next) {
+          issue_qk(1, s_next);
+        } else {
+          tc_commit(&o_full[1]);
+        }
+        s = s_next;
+        phase = phase_next;
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int wg = (warp - 2) >> 2;       // 0 or 1: which query tile
+    const int quarter = warp & 3;         // TMEM lane quarter accessible to this warp
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + wg * ATT_BQ + row_in_tile;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_s[wg] + lane_sel;
+    const uint32_t o_addr = tmem_o[wg] + lane_sel;
+    uint8_t* sp_row = smem + L::P_OFF + wg * L::P_TILE_BYTES + row_in_tile * 128;
+    const int sw = row_in_tile & 7;
+
+    float m_used = -INFINITY;  // max (raw score units) the stored exponentials are relative to
+    float row_sum = 0.f;
+    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * ATT_BK;  // valid keys in the last tile of each chunk
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      float sc[ATT_BK];
+      tmem_ld_x32f(s_addr, sc);
+      tmem_ld_x32f(s_addr + 32, sc + 32);
+      tmem_wait_ld();
+      const int jj = j % tiles_per_chunk;
+      if (jj == tiles_per_chunk - 1 && last_valid < ATT_BK) {
+#pragma unroll
+        for (int c = 0; c < ATT_BK; ++c)
+          if (c >= last_valid) sc[c] = -INFINITY;
+      }
+      float mx = sc[0];
+#pragma unroll
+      for (int c = 1; c < ATT_BK; ++c) mx = fmaxf(mx, sc[c]);
+      const float m_new = fmaxf(m_used, mx);
+      // lazy rescale: keep the old reference max unless it is stale by more than 2^8
+      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;  // also true on the first tile (m_used = -inf)
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
+        if (need) {
+          m_used = m_new;
+          row_sum *= alpha;
+        }
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float ov[32];
+          tmem_ld_x32f(o_addr + c, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
+          tmem_st_x32f(o_addr + c, ov);
+        }
+        tmem_wait_st();
+      }
+      const float mb = m_used * p.scale_log2;
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < ATT_BK; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          e[t] = ex2_approx(fmaf(sc[c + t], p.scale_log2, -mb));
+          psum += e[t];
+        }
+        uint4 pk;
+        pk.x = pack_bf16(e[0], e[1]);
+        pk.y = pack_bf16(e[2], e[3]);
+        pk.z = pack_bf16(e[4], e[5]);
+        pk.w = pack_bf16(e[6], e[7]);
+        // 128B-swizzled K-major row: 16-byte chunk index XOR (row % 8)
+        *reinterpret_cast<uint4*>(sp_row + (((c >> 3) ^ sw) << 4)) = pk;
+      }
+      row_sum += psum;
+      fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      mbar_arrive(&p_ready[wg]);
+    }
+
+    // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d)
+    mbar_wait(&o_full[wg], 0);
+    tc_fence_after();
+    const float inv = 1.0f / row_sum;
+    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + (long long)q_row * p.o_stride_s;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      float ov[32];
+      tmem_ld_x32f(o_addr + c, ov);
+      tmem_wait_ld();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
+          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
+          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
+          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c + t) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, int STAGES>
+static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
+  using L = AttnSmem<D, STAGES>;
+  CUtensorMap tmQ, tmK, tmV;
+  const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
+  const int sk_chunk = chunks > 1 ? a->sk_chunk : a->sk;
+  {
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->sq, (uint64_t)a->heads, (uint64_t)a->batch};
+    uint64_t str[3] = {(uint64_t)a->q_stride_s * 2, (uint64_t)a->q_stride_h * 2, (uint64_t)a->q_stride_b * 2};
+    uint32_t box[4] = {64, ATT_BQ, 1, 1};
+    int r = encode_tmap_bf16(&tmQ, a->q, 4, dims, str, box);
+    if (r) return r;
+  }
+  // K/V: the outermost tensor-map coordinate enumerates (batch, chunk); with one chunk it is just the batch.
+  // Chunked K/V (frame-sharded window) needs b-stride == kv_chunks * chunk-stride so the two collapse into one dim.
+  auto enc_kv = [&](CUtensorMap* tm, const void* base, int64_t ss, int64_t sh, int64_t sb, int64_t schunk) -> int {
+    int64_t outer_stride = sb;
+    if (chunks > 1) {
+      if (a->batch > 1 && sb != schunk * chunks) {
+        set_last_error("flash_attn: kv_chunks > 1 requires b-stride == kv_chunks * chunk-stride (got %lld vs %lld)",
+                       (long long)sb, (long long)(schunk * chunks));
+        return AMB_ERR_UNSUPPORTED;
+      }
+      outer_stride = schunk;
+    }
+    uint64_t dims[4] = {(uint64_t)D, (uint64_t)sk_chunk, (uint64_t)a->heads, (uint64_t)a->batch * chunks};
+    uint64_t str[3] = {(uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)outer_stride * 2};
+    uint32_t box[4] = {64, ATT_BK, 1, 1};
+    return encode_tmap_bf16(tm, base, 4, dims, str, box);
+  };
+  int r = enc_kv(&tmK, a->k, a->k_stride_s, a->k_stride_h, a->k_stride_b, a->k_chunk_stride);
+  if (r) return r;
+  r = enc_kv(&tmV, a->v, a->v_stride_s, a->v_stride_h, a->v_stride_b, a->v_chunk_stride);
+  if (r) return r;
+
+  AttnParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(a->o);
+  p.o_stride_b = a->o_stride_b; p.o_stride_h = a->o_stride_h; p.o_stride_s = a->o_stride_s;
+  p.heads = a->heads; p.sq = a->sq; p.sk = a->sk;
+  p.kv_chunks = chunks; p.sk_chunk = sk_chunk;
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+
+  auto kern = flash_attn_fwd_kernel<D, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
+  kern<<<grid, ATT_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
+  AMB_CHECK_ARG(a && a->q && a->k && a->v && a->o, "flash_attn: null pointer");
+  AMB_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->sq > 0 && a->sk > 0, "flash_attn: bad shape b=%d h=%d sq=%d sk=%d",
+                a->batch, a->heads, a->sq, a->sk);
+  AMB_CHECK_ARG(a->head_dim == 128 || a->head_dim == 64, "flash_attn: head_dim %d unsupported (64 or 128)", a->head_dim);
+  AMB_CHECK_ARG(a->q_stride_s % 8 == 0 && a->k_stride_s % 8 == 0 && a->v_stride_s % 8 == 0 && a->o_stride_s % 8 == 0 &&
+                    a->q_stride_h % 8 == 0 && a->k_stride_h % 8 == 0 && a->v_stride_h % 8 == 0 && a->o_stride_h % 8 == 0 &&
+                    a->q_stride_b % 8 == 0 && a->k_stride_b % 8 == 0 && a->v_stride_b % 8 == 0 && a->o_stride_b % 8 == 0,
+                "flash_attn: strides must be multiples of 8 elements (16 bytes)");
+  AMB_CHECK_ARG(a->kv_chunks <= 1 || (a->sk_chunk > 0 && (int64_t)a->sk_chunk * a->kv_chunks == a->sk),
+                "flash_attn: kv_chunks * sk_chunk must equal sk");
+  AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->head_dim == 128) return launch_attn<128, 3>(a, s);
+  return launch_attn<64, 4>(a, s);
+}

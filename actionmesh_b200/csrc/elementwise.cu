@@ -1,0 +1,276 @@
+// HBM-bound elementwise / row-reduction kernels of the denoising path (sm_100a).
+//  - cfg_euler_step : CFG combine + Euler flow update + observed-frame mask   (scheduler.py:238-248, guidance.py:95-118)
+//  - layernorm      : affine LayerNorm with fp32 statistics                    (block.py:64,83,98,107)
+//  - cast / timestep embedding / bias-row add
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/actionmesh_b200.h"
+
+namespace amb {
+
+// ------------------------------------------------------------------------------------------------ K9
+constexpr int kMaxBranches = 4;
+struct CfgEulerParams {
+  float* latents;
+  const __nv_bfloat16* pred;
+  const uint8_t* frame_update;
+  float scales[kMaxBranches];
+  float dt;
+  int n_branches;
+  int n_frames;
+  long long n_per_frame;  // multiple of 4
+  long long branch_stride, frame_stride, frame_offset;
+};
+
+// One thread = 4 consecutive latent elements: 16 B fp32 read + 8 B per bf16 branch read + 16 B write, all coalesced.
+__global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) {
+  const long long vec_per_frame = p.n_per_frame >> 2;
+  const long long total = vec_per_frame * p.n_frames;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i / vec_per_frame);
+    if (!p.frame_update[f]) continue;  // observed frame: bit-identical pass-through (scheduler.py:244-246)
+    const long long e = (i - (long long)f * vec_per_frame) << 2;
+    float4* xp = reinterpret_cast<float4*>(p.latents + (long long)f * p.n_per_frame + e);
+    const __nv_bfloat16* pp = p.pred + (long long)f * p.frame_stride + p.frame_offset + e;
+    float4 x = *xp;
+    uint2 raw = __ldg(reinterpret_cast<const uint2*>(pp));
+    float2 a01 = unpack_bf16(raw.x), a23 = unpack_bf16(raw.y);
+    float v0 = a01.x, v1 = a01.y, v2 = a23.x, v3 = a23.y;
+    float q0 = v0, q1 = v1, q2 = v2, q3 = v3;  // previous branch
+#pragma unroll
+    for (int k = 1; k < kMaxBranches; ++k) {
+      if (k < p.n_branches) {
+        uint2 r = __ldg(reinterpret_cast<const uint2*>(pp + (long long)k * p.branch_stride));
+        float2 b01 = unpack_bf16(r.x), b23 = unpack_bf16(r.y);
+        const float s = p.scales[k - 1];
+        v0 += s * (b01.x - q0);
+        v1 += s * (b01.y - q1);
+        v2 += s * (b23.x - q2);
+        v3 += s * (b23.y - q3);
+        q0 = b01.x; q1 = b01.y; q2 = b23.x; q3 = b23.y;
+      }
+    }
+    x.x += p.dt * v0;
+    x.y += p.dt * v1;
+    x.z += p.dt * v2;
+    x.w += p.dt * v3;
+    *xp = x;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// One warp per row; the row (<= 4096 elements) is held in registers between the statistics and the normalise pass, so
+// HBM sees exactly one read and one write of the row.  Two-pass (mean, then centred variance) in fp32 like
+// F.layer_norm on an fp32 upcast.
+template <int COLS, bool XF32>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, long long ldx,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        long long ldy, long long rows, float eps) {
+  constexpr int PER_LANE = COLS / 32;   // elements per lane
+  constexpr int VEC = PER_LANE / 8;     // 8-element vectors per lane
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  float v[PER_LANE];
+  if constexpr (XF32) {
+    const float* x = reinterpret_cast<const float*>(xv) + row * ldx;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      const float4* p4 = reinterpret_cast<const float4*>(x + (j * 32 + lane) * 8);
+      float4 a = __ldg(p4), b = __ldg(p4 + 1);
+      v[j * 8 + 0] = a.x; v[j * 8 + 1] = a.y; v[j * 8 + 2] = a.z; v[j * 8 + 3] = a.w;
+      v[j * 8 + 4] = b.x; v[j * 8 + 5] = b.y; v[j * 8 + 6] = b.z; v[j * 8 + 7] = b.w;
+    }
+  } else {
+    const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(xv) + row * ldx;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      uint4 r = __ldg(reinterpret_cast<const uint4*>(x + (j * 32 + lane) * 8));
+      float2 f0 = unpack_bf16(r.x), f1 = unpack_bf16(r.y), f2 = unpack_bf16(r.z), f3 = unpack_bf16(r.w);
+      v[j * 8 + 0] = f0.x; v[j * 8 + 1] = f0.y; v[j * 8 + 2] = f1.x; v[j * 8 + 3] = f1.y;
+      v[j * 8 + 4] = f2.x; v[j * 8 + 5] = f2.y; v[j * 8 + 6] = f3.x; v[j * 8 + 7] = f3.y;
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER_LANE; ++j) s += v[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < PER_LANE; ++j) {
+    const float d = v[j] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / COLS) + eps);
+  __nv_bfloat16* yr = y + row * ldy;
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int c = (j * 32 + lane) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    uint4 o;
+    o.x = pack_bf16((v[j * 8 + 0] - mean) * rstd * g0.x + b0.x, (v[j * 8 + 1] - mean) * rstd * g0.y + b0.y);
+    o.y = pack_bf16((v[j * 8 + 2] - mean) * rstd * g0.z + b0.z, (v[j * 8 + 3] - mean) * rstd * g0.w + b0.w);
+    o.z = pack_bf16((v[j * 8 + 4] - mean) * rstd * g1.x + b1.x, (v[j * 8 + 5] - mean) * rstd * g1.y + b1.y);
+    o.w = pack_bf16((v[j * 8 + 6] - mean) * rstd * g1.z + b1.z, (v[j * 8 + 7] - mean) * rstd * g1.w + b1.w);
+    *reinterpret_cast<uint4*>(yr + c) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            long long n) {
+  const long long n4 = n >> 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 o;
+    o.x = pack_bf16(a.x, a.y);
+    o.y = pack_bf16(a.z, a.w);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+  // tail (n % 4)
+  const long long tail0 = n4 << 2;
+  for (long long i = tail0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// diffusers Timesteps(flip_sin_to_cos=False, downscale_freq_shift=0): [sin(t w_j) | cos(t w_j)], w_j = exp(-ln(1e4) j / half)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int rows, int channels,
+                                          __nv_bfloat16* __restrict__ out) {
+  const int half = channels >> 1;
+  const int r = blockIdx.x;
+  const float tv = t[r];
+  for (int j = threadIdx.x; j < half; j += blockDim.x) {
+    const float w = expf(-9.210340371976184f * (float)j / (float)half);
+    const float a = tv * w;
+    out[(long long)r * channels + j] = __float2bfloat16_rn(sinf(a));
+    out[(long long)r * channels + half + j] = __float2bfloat16_rn(cosf(a));
+  }
+}
+
+__global__ void __launch_bounds__(256) add_bias_rows_kernel(__nv_bfloat16* __restrict__ y, long long ldy,
+                                                            const float* __restrict__ bias, long long rows, int cols) {
+  const int vec_per_row = cols >> 3;
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row) << 3;
+    uint4* p = reinterpret_cast<uint4*>(y + r * ldy + c);
+    uint4 raw = *p;
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+    float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
+    raw.x = pack_bf16(f0.x + b0.x, f0.y + b0.y);
+    raw.y = pack_bf16(f1.x + b0.z, f1.y + b0.w);
+    raw.z = pack_bf16(f2.x + b1.x, f2.y + b1.y);
+    raw.w = pack_bf16(f3.x + b1.z, f3.y + b1.w);
+    *p = raw;
+  }
+}
+
+static int grid_for(long long work_items, int block) {
+  long long g = (work_items + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;  // grid-stride loops; a few waves of resident CTAs
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" {
+
+int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, const float* scales_host,
+                       float dt_signed, const uint8_t* frame_update, int n_frames, int64_t n_per_frame,
+                       int64_t branch_stride, int64_t frame_stride, int64_t frame_offset, amb_stream_t stream) {
+  AMB_CHECK_ARG(latents && pred_bf16 && frame_update, "cfg_euler_step: null pointer");
+  AMB_CHECK_ARG(n_branches >= 1 && n_branches <= kMaxBranches, "cfg_euler_step: n_branches %d not in [1,%d]", n_branches, kMaxBranches);
+  AMB_CHECK_ARG(n_branches == 1 || scales_host, "cfg_euler_step: scales required");
+  AMB_CHECK_ARG(n_per_frame % 4 == 0 && frame_stride % 4 == 0 && frame_offset % 4 == 0 && branch_stride % 4 == 0,
+                "cfg_euler_step: sizes/strides must be multiples of 4 elements");
+  AMB_CHECK_ARG((reinterpret_cast<uintptr_t>(latents) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred_bf16) & 7) == 0,
+                "cfg_euler_step: misaligned pointers");
+  if (n_frames <= 0 || n_per_frame <= 0) return AMB_OK;
+  CfgEulerParams p;
+  p.latents = latents;
+  p.pred = reinterpret_cast<const __nv_bfloat16*>(pred_bf16);
+  p.frame_update = frame_update;
+  for (int i = 0; i < kMaxBranches; ++i) p.scales[i] = (i < n_branches - 1) ? scales_host[i] : 0.f;
+  p.dt = dt_signed;
+  p.n_branches = n_branches;
+  p.n_frames = n_frames;
+  p.n_per_frame = n_per_frame;
+  p.branch_stride = branch_stride;
+  p.frame_stride = frame_stride;
+  p.frame_offset = frame_offset;
+  const long long vecs = (n_per_frame >> 2) * (long long)n_frames;
+  cfg_euler_kernel<<<grid_for(vecs, 256), 256, 0, (cudaStream_t)stream>>>(p);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                  int64_t ldy, int64_t rows, int cols, float eps, amb_stream_t stream) {
+  AMB_CHECK_ARG(x && gamma && beta && y_bf16, "layernorm: null pointer");
+  AMB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: row strides must be multiples of 8 elements");
+  if (rows <= 0) return AMB_OK;
+  const int wpb = 8;
+  dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
+  cudaStream_t s = (cudaStream_t)stream;
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define AMB_LN_CASE(C)                                                                                           \
+  case C:                                                                                                        \
+    if (x_fp32) layernorm_kernel<C, true><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);         \
+    else layernorm_kernel<C, false><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);               \
+    break;
+  switch (cols) {
+    AMB_LN_CASE(256)
+    AMB_LN_CASE(512)
+    AMB_LN_CASE(1024)
+    AMB_LN_CASE(2048)
+    AMB_LN_CASE(4096)
+    default:
+      set_last_error("layernorm: unsupported cols %d (256/512/1024/2048/4096)", cols);
+      return AMB_ERR_UNSUPPORTED;
+  }
+#undef AMB_LN_CASE
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, amb_stream_t stream) {
+  AMB_CHECK_ARG(src && dst_bf16, "cast: null pointer");
+  AMB_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_bf16) & 7) == 0, "cast: misaligned");
+  if (n <= 0) return AMB_OK;
+  cast_f32_bf16_kernel<<<grid_for((n + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_timestep_embedding(const float* t, int rows, int channels, void* out_bf16, amb_stream_t stream) {
+  AMB_CHECK_ARG(t && out_bf16, "timestep_embedding: null pointer");
+  AMB_CHECK_ARG(channels % 2 == 0 && channels > 0, "timestep_embedding: channels must be even");
+  if (rows <= 0) return AMB_OK;
+  timestep_embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(t, rows, channels, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream) {
+  AMB_CHECK_ARG(y_bf16 && bias, "add_bias_rows: null pointer");
+  AMB_CHECK_ARG(cols % 8 == 0 && ldy % 8 == 0, "add_bias_rows: cols/ldy must be multiples of 8");
+  if (rows <= 0) return AMB_OK;
+  add_bias_rows_kernel<<<grid_for(rows * (cols >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, bias, rows, cols);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// tcgen05 GEMM for sm_100a:  C = epilogue(A · Wᵀ),  A:(M,K) bf16, W:(N,K) bf16 (nn.Linear layout), fp32 accumulate in TMEM.
+//
+// Persistent, warp-specialised:
+//   warp 0      TMA producer   (one elected lane; cp.async.bulk.tensor 2D, 128B swizzle, STAGES-deep mbarrier ring)
+//   warp 1      MMA issuer     (one lane issues tcgen05.mma cta_group::1 128xBNx16; owns the TMEM allocation)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread == accumulator row; bias / GELU / LayerScale / residual /
+//                               per-head RMSNorm + RoPE; 16-byte global stores)
+// Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
+// Tiles are visited n-fastest so the CTAs of one wave share A rows through L2 and W stays L2-resident.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "../../include/actionmesh_b200.h"
+
+namespace amb {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
+
+struct GemmParams {
+  int M, N, K;
+  int k_split_blocks;  // k-blocks >= this come from the second A source (INT_MAX: single source)
+  void* C;
+  long long ldc;
+  int c_fp32;
+  const float* bias;
+  const void* residual;
+  long long ldr;
+  int res_fp32;
+  int act;
+  const float* col_scale;
+  int grp_rows, grp_stride, row_off;
+  int norm_cols, norm_seg;
+  const float* norm_w0;
+  const float* norm_w1;
+  float norm_eps;
+  int rope_cols;
+  const float* rope_cos;
+  const float* rope_sin;
+  int rope_rows_per_pos;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;  // + alignment slack
+};
+
+// store 8 consecutive output columns of one row (values already final)
+__device__ __forceinline__ void store8(void* C, int c_fp32, long long off, const float* v) {
+  if (c_fp32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]);
+    o.y = pack_bf16(v[2], v[3]);
+    o.z = pack_bf16(v[4], v[5]);
+    o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(C) + off) = o;
+  }
+}
+__device__ __forceinline__ void load8_residual(const void* R, int r_fp32, long long off, float* r) {
+  if (r_fp32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(R) + off);
+    float4 a = p[0], b = p[1];
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+  } else {
+    uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(R) + off);
+    float2 f0 = unpack_bf16(raw.x), f1 = unpack_bf16(raw.y), f2 = unpack_bf16(raw.z), f3 = unpack_bf16(raw.w);
+    r[0] = f0.x; r[1] = f0.y; r[2] = f1.x; r[3] = f1.y; r[4] = f2.x; r[5] = f2.y; r[6] = f3.x; r[7] = f3.y;
+  }
+}
+
+// bias -> activation -> column scale -> residual -> store, for `NV` (multiple of 8) consecutive columns starting at col
+template <int NV>
+__device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, long long drow, int col, bool valid) {
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col + j));
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (p.col_scale) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4) {
+      const float4 s = __ldg(reinterpret_cast<const float4*>(p.col_scale + col + j));
+      v[j] *= s.x; v[j + 1] *= s.y; v[j + 2] *= s.z; v[j + 3] *= s.w;
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int j = 0; j < NV; j += 8) {
+    if (p.residual) {
+      float r[8];
+      load8_residual(p.residual, p.res_fp32, drow * p.ldr + col + j, r);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[j + t] += r[t];
+    }
+    store8(p.C, p.c_fp32, drow * p.ldc + col + j, v + j);
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = GemmSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full[a], 1);
+        mbar_init(&tmem_empty[a], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_n_tiles = p.N / BN;
+  const int num_m_tiles = (p.M + BM - 1) / BM;
+  const int num_tiles = num_n_tiles * num_m_tiles;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int s = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n_tiles) * BM;
+        const int n0 = (tile % num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (kb < p.k_split_blocks) tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0, kEvictNormal);
+          else tma_load_2d(sa, &tmA2, &full_bar[s], (kb - p.k_split_blocks) * BK, m0, kEvictNormal);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0, kEvictLast);
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+      int s = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            mma_ss(d_tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32), idesc,
+                   (kb | k) != 0);
+          }
+          tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / num_n_tiles) * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      const int row = m0 + row_in_tile;
+      const bool valid = row < p.M;
+      long long drow = row;
+      if (p.grp_rows > 0) drow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows) + p.row_off;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+
+      if (n0 < p.norm_cols) {
+        // ---- per-head RMSNorm (+ RoPE): one head = 128 accumulator columns, all owned by this thread ----
+        if constexpr (BN % 128 == 0) {
+#pragma unroll 1
+          for (int hc = 0; hc < BN; hc += 128) {
+            const int col0 = n0 + hc;
+            float v[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld_x32f(taddr + hc + c * 32, v + c * 32);
+            tmem_wait_ld();
+            if (col0 < p.norm_cols) {
+              float ss = 0.f;
+#pragma unroll
+              for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
+              const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+              const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
+#pragma unroll
+              for (int j = 0; j < 128; j += 4) {
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
+                v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
+              }
+              if (col0 < p.rope_cols) {
+                const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
+                const float* cs = p.rope_cos + (long long)pos * 64;
+                const float* sn = p.rope_sin + (long long)pos * 64;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + j));
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + j));
+                  float a, b;
+                  a = v[2 * j + 0]; b = v[2 * j + 1]; v[2 * j + 0] = a * c4.x - b * s4.x; v[2 * j + 1] = b * c4.x + a * s4.x;
+                  a = v[2 * j + 2]; b = v[2 * j + 3]; v[2 * j + 2] = a * c4.y - b * s4.y; v[2 * j + 3] = b * c4.y + a * s4.y;
+                  a = v[2 * j + 4]; b = v[2 * j + 5]; v[2 * j + 4] = a * c4.z - b * s4.z; v[2 * j + 5] = b * c4.z + a * s4.z;
+                  a = v[2 * j + 6]; b = v[2 * j + 7]; v[2 * j + 6] = a * c4.w - b * s4.w; v[2 * j + 7] = b * c4.w + a * s4.w;
+                }
+              }
+            } else if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 128; j += 4) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 128; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col0 + j, v + j);
+            }
+          }
+        }
+      } else {
+        // ---- plain epilogue in 32-column chunks ----
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          tmem_ld_x32f(taddr + c, v);
+          tmem_wait_ld();
+          finish_and_store<32>(p, v, drow, n0 + c, valid);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const amb_gemm_args* a, cudaStream_t stream) {
+  using L = GemmSmem<BN, STAGES>;
+  CUtensorMap tmA, tmA2, tmB;
+  const int k1 = (a->a2 != nullptr) ? a->k_split : a->k;
+  {
+    uint64_t dims[2] = {(uint64_t)k1, (uint64_t)a->m};
+    uint64_t str[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int r = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box);
+    if (r) return r;
+  }
+  if (a->a2) {
+    uint64_t dims[2] = {(uint64_t)(a->k - a->k_split), (uint64_t)a->m};
+    uint64_t str[1] = {(uint64_t)a->lda2 * 2};
+    uint32_t box[2] = {BK, BM};
+    int r = encode_tmap_bf16(&tmA2, a->a2, 2, dims, str, box);
+    if (r) return r;
+  } else {
+    tmA2 = tmA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+    uint64_t str[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {BK, BN};
+    int r = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box);
+    if (r) return r;
+  }
+  GemmParams p;
+  p.M = a->m; p.N = a->n; p.K = a->k;
+  p.k_split_blocks = a->a2 ? a->k_split / BK : 0x7fffffff;
+  p.C = a->c; p.ldc = a->ldc; p.c_fp32 = a->c_fp32;
+  p.bias = a->bias;
+  p.residual = a->residual; p.ldr = a->ldr; p.res_fp32 = a->res_fp32;
+  p.act = a->act;
+  p.col_scale = a->col_scale;
+  p.grp_rows = a->grp_rows; p.grp_stride = a->grp_stride; p.row_off = a->row_off;
+  p.norm_cols = a->norm_cols; p.norm_seg = a->norm_seg;
+  p.norm_w0 = a->norm_w0; p.norm_w1 = a->norm_w1 ? a->norm_w1 : a->norm_w0;
+  p.norm_eps = a->norm_eps;
+  p.rope_cols = a->rope_cols; p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
+  p.rope_rows_per_pos = a->rope_rows_per_pos > 0 ? a->rope_rows_per_pos : 1;
+
+  auto kern = gemm_bf16_kernel<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int num_tiles = (a->n / BN) * ((a->m + BM - 1) / BM);
+  int grid = num_sms();
+  if (grid > num_tiles) grid = num_tiles;
+  kern<<<grid, 192, L::TOTAL, stream>>>(tmA, tmA2, tmB, p);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+}  // namespace amb
+
+using namespace amb;
+
+extern "C" int amb_gemm_bf16(const amb_gemm_args* a, amb_stream_t stream) {
+  AMB_CHECK_ARG(a && a->a && a->w && a->c, "gemm: null pointer");
+  AMB_CHECK_ARG(a->m > 0 && a->n > 0 && a->k > 0, "gemm: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+  AMB_CHECK_ARG(a->k % BK == 0, "gemm: k=%d must be a multiple of %d", a->k, BK);
+  AMB_CHECK_ARG(a->n % 64 == 0, "gemm: n=%d must be a multiple of 64", a->n);
+  AMB_CHECK_ARG(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->ldc % 8 == 0, "gemm: lda/ldw/ldc must be multiples of 8 elements");
+  AMB_CHECK_ARG(!a->a2 || (a->k_split > 0 && a->k_split < a->k && a->k_split % BK == 0 && a->lda2 % 8 == 0),
+                "gemm: bad k_split %d", a->k_split);
+  AMB_CHECK_ARG(!a->residual || a->ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
+  AMB_CHECK_ARG(a->act == 0 || a->act == 1, "gemm: unknown activation %d", a->act);
+  if (a->norm_cols > 0) {
+    AMB_CHECK_ARG(a->n % 128 == 0 && a->norm_cols % 128 == 0 && a->norm_w0, "gemm: head epilogue needs n %% 128 == 0 and norm weights");
+    AMB_CHECK_ARG(a->norm_seg % 128 == 0, "gemm: norm_seg must be a multiple of 128");
+    AMB_CHECK_ARG(a->rope_cols % 128 == 0 && a->rope_cols <= a->norm_cols, "gemm: rope_cols must be a multiple of 128 and <= norm_cols");
+    AMB_CHECK_ARG(a->rope_cols == 0 || (a->rope_cos && a->rope_sin), "gemm: rope tables required");
+    AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale, "gemm: head epilogue excludes residual/activation/col_scale");
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (a->n % 256 == 0) return launch_gemm<256, 4>(a, s);
+  if (a->n % 128 == 0) return launch_gemm<128, 6>(a, s);
+  return launch_gemm<64, 8>(a, s);
+}

@@ -1,0 +1,206 @@
+"""Torch-tensor front door to the C ABI (device pointers + the current CUDA stream; torch is only plumbing here).
+
+Every function launches hand-written sm_100a kernels from libactionmesh_b200.so; nothing here computes with torch ops.
+A global launch counter (`launch_count`) lets bench.py report how many of OUR kernels ran in the timed region.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _need(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise _lib.AmbError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.AmbError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def cfg_euler_step(latents: torch.Tensor, pred: torch.Tensor, scales: list[float], dt_signed: float,
+                   frame_update: torch.Tensor, *, n_branches: int, branch_stride: int, frame_stride: int,
+                   frame_offset: int, n_per_frame: int) -> None:
+    """In-place x[f] += dt * (p0 + sum_i s_i (p_{i+1} - p_i)) on frames with frame_update[f] != 0.
+
+    Replaces guidance.py:95-118 + scheduler.py:238-248 of the reference."""
+    global launch_count
+    _need(latents, torch.float32, "latents")
+    _need(pred, torch.bfloat16, "pred")
+    _need(frame_update, torch.uint8, "frame_update")
+    n_frames = frame_update.numel()
+    arr = (C.c_float * max(1, len(scales)))(*scales)
+    rc = _lib.load_library().amb_cfg_euler_step(
+        latents.data_ptr(), pred.data_ptr(), n_branches, arr, float(dt_signed), frame_update.data_ptr(), n_frames,
+        n_per_frame, branch_stride, frame_stride, frame_offset, _stream())
+    _lib.check(rc, "amb_cfg_euler_step")
+    launch_count += 1
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Affine LayerNorm over the last dim of a 2-D (rows, cols) tensor, fp32 statistics, bf16 output."""
+    global launch_count
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, cols = x.shape
+    if out is None:
+        out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    _need(gamma, torch.float32, "gamma")
+    _need(beta, torch.float32, "beta")
+    _need(out, torch.bfloat16, "out")
+    if x.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.AmbError(f"layernorm: unsupported dtype {x.dtype}")
+    rc = _lib.load_library().amb_layernorm(
+        x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+        out.stride(0), rows, cols, float(eps), _stream())
+    _lib.check(rc, "amb_layernorm")
+    launch_count += 1
+    return out
+
+
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    _need(src, torch.float32, "src")
+    assert src.is_contiguous()
+    if out is None:
+        out = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    rc = _lib.load_library().amb_cast_f32_bf16(src.data_ptr(), out.data_ptr(), src.numel(), _stream())
+    _lib.check(rc, "amb_cast_f32_bf16")
+    launch_count += 1
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global launch_count
+    _need(t, torch.float32, "t")
+    rows = t.numel()
+    if out is None:
+        out = torch.empty((rows, channels), dtype=torch.bfloat16, device=t.device)
+    rc = _lib.load_library().amb_timestep_embedding(t.data_ptr(), rows, channels, out.data_ptr(), _stream())
+    _lib.check(rc, "amb_timestep_embedding")
+    launch_count += 1
+    return out
+
+
+def add_bias_rows(y: torch.Tensor, bias: torch.Tensor) -> None:
+    global launch_count
+    _need(y, torch.bfloat16, "y")
+    _need(bias, torch.float32, "bias")
+    assert y.dim() == 2 and y.stride(1) == 1
+    rc = _lib.load_library().amb_add_bias_rows(y.data_ptr(), y.stride(0), bias.data_ptr(), y.shape[0], y.shape[1], _stream())
+    _lib.check(rc, "amb_add_bias_rows")
+    launch_count += 1
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         a2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
+         col_scale: Optional[torch.Tensor] = None, row_map: Optional[tuple[int, int, int]] = None,
+         norm: Optional[dict] = None) -> torch.Tensor:
+    """out = epilogue(cat[a, a2] @ w.T).  a:(m,k1) bf16, a2:(m,k2) bf16 or None, w:(n,k1+k2) bf16, out bf16/fp32.
+
+    norm = dict(cols=, seg=, w0=, w1=, eps=, rope_cols=, cos=, sin=, rows_per_pos=) enables the per-head
+    RMSNorm(+RoPE) epilogue of attention_processor.py:106-130."""
+    global launch_count
+    _need(a, torch.bfloat16, "a")
+    _need(w, torch.bfloat16, "w")
+    assert a.dim() == 2 and w.dim() == 2 and out.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and out.stride(1) == 1
+    g = _lib.GemmArgs()
+    m, k1 = a.shape
+    n, k = w.shape
+    g.a, g.lda = a.data_ptr(), a.stride(0)
+    if a2 is not None:
+        _need(a2, torch.bfloat16, "a2")
+        assert a2.shape[0] == m and a2.stride(1) == 1 and k1 + a2.shape[1] == k
+        g.a2, g.lda2, g.k_split = a2.data_ptr(), a2.stride(0), k1
+    else:
+        assert k1 == k, f"a has k={k1}, w has k={k}"
+        g.a2, g.lda2, g.k_split = None, 0, 0
+    g.w, g.ldw = w.data_ptr(), w.stride(0)
+    if out.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.AmbError(f"gemm: unsupported output dtype {out.dtype}")
+    g.c, g.ldc, g.c_fp32 = out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
+    g.m, g.n, g.k = m, n, k
+    if bias is not None:
+        _need(bias, torch.float32, "bias")
+    g.bias = _ptr(bias)
+    if residual is not None:
+        assert residual.stride(1) == 1
+        g.residual, g.ldr, g.res_fp32 = residual.data_ptr(), residual.stride(0), int(residual.dtype == torch.float32)
+    else:
+        g.residual, g.ldr, g.res_fp32 = None, 0, 0
+    g.act = act
+    if col_scale is not None:
+        _need(col_scale, torch.float32, "col_scale")
+    g.col_scale = _ptr(col_scale)
+    if row_map is not None:
+        g.grp_rows, g.grp_stride, g.row_off = row_map
+    else:
+        g.grp_rows = g.grp_stride = g.row_off = 0
+    if norm is not None:
+        g.norm_cols, g.norm_seg = norm["cols"], norm.get("seg", norm["cols"])
+        g.norm_w0 = norm["w0"].data_ptr()
+        g.norm_w1 = norm["w1"].data_ptr() if norm.get("w1") is not None else None
+        g.norm_eps = float(norm["eps"])
+        g.rope_cols = norm.get("rope_cols", 0)
+        g.rope_cos = _ptr(norm.get("cos"))
+        g.rope_sin = _ptr(norm.get("sin"))
+        g.rope_rows_per_pos = norm.get("rows_per_pos", 1)
+    else:
+        g.norm_cols = g.norm_seg = g.rope_cols = 0
+        g.norm_w0 = g.norm_w1 = g.rope_cos = g.rope_sin = None
+        g.norm_eps = 0.0
+        g.rope_rows_per_pos = 1
+    rc = _lib.load_library().amb_gemm_bf16(C.byref(g), _stream())
+    _lib.check(rc, "amb_gemm_bf16")
+    launch_count += 1
+    return out
+
+
+def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float, *,
+               kv_chunks: int = 1) -> torch.Tensor:
+    """softmax(scale q kᵀ) v, non-causal.  q:(B,Sq,H,D) k,v:(B,Sk,H,D) out:(B,Sq,H,D) — arbitrary (16-byte aligned)
+    strides with unit stride on D, so views into a fused QKV buffer work in place.
+
+    With kv_chunks > 1, k/v are (B, chunks, Sk_chunk, H, D) (rank-c all-gathered K/V of the frame-sharded window)."""
+    global launch_count
+    for t, nme in ((q, "q"), (k, "k"), (v, "v"), (out, "out")):
+        _need(t, torch.bfloat16, nme)
+        assert t.stride(-1) == 1
+    a = _lib.AttnArgs()
+    B, Sq, H, D = q.shape
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.q_stride_b, a.q_stride_s, a.q_stride_h = q.stride(0), q.stride(1), q.stride(2)
+    a.o_stride_b, a.o_stride_s, a.o_stride_h = out.stride(0), out.stride(1), out.stride(2)
+    if kv_chunks > 1:
+        assert k.dim() == 5 and v.dim() == 5 and k.shape[1] == kv_chunks
+        a.k_stride_b, a.k_chunk_stride, a.k_stride_s, a.k_stride_h = k.stride(0), k.stride(1), k.stride(2), k.stride(3)
+        a.v_stride_b, a.v_chunk_stride, a.v_stride_s, a.v_stride_h = v.stride(0), v.stride(1), v.stride(2), v.stride(3)
+        a.sk_chunk = k.shape[2]
+        a.sk = k.shape[1] * k.shape[2]
+    else:
+        assert k.dim() == 4 and v.dim() == 4
+        a.k_stride_b, a.k_stride_s, a.k_stride_h = k.stride(0), k.stride(1), k.stride(2)
+        a.v_stride_b, a.v_stride_s, a.v_stride_h = v.stride(0), v.stride(1), v.stride(2)
+        a.k_chunk_stride = a.v_chunk_stride = 0
+        a.sk_chunk = k.shape[1]
+        a.sk = k.shape[1]
+    a.kv_chunks = kv_chunks
+    a.batch, a.heads, a.sq, a.head_dim = B, H, Sq, D
+    a.scale = float(scale)
+    rc = _lib.load_library().amb_flash_attn_fwd(C.byref(a), _stream())
+    _lib.check(rc, "amb_flash_attn_fwd")
+    launch_count += 1
+    return out

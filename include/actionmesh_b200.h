@@ -1,0 +1,136 @@
+/*
+ * actionmesh_b200 — C ABI of the B200-native (sm_100a) Stage-I denoising hot path of ActionMesh.
+ *
+ * The reference (facebookresearch/actionmesh) is pure Python on top of PyTorch library kernels; it has no FFI of its
+ * own.  Each entry point below therefore cites the reference *call site* whose arithmetic it replaces (paths relative
+ * to the reference checkout).  The Python host side (actionmesh_b200/*.py) binds these with ctypes and mirrors the
+ * reference's operator interfaces (AttentionProcessor.__call__, ActionMeshDenoiser.forward, SchedulerFlow.denoise,
+ * ImageEncoder.encode_images); see INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative amb error code otherwise; amb_last_error() gives the message;
+ *  - plain pointers and sizes only (no torch types); all pointers are DEVICE pointers unless stated;
+ *  - the caller allocates every output; the library keeps no caller memory;
+ *  - every launch is asynchronous on the given cudaStream_t (passed as void*); no hidden synchronisation;
+ *  - bf16 tensors are passed as const void* / void* (uint16 storage);
+ *  - "ld*" arguments are row strides in ELEMENTS.
+ */
+#ifndef ACTIONMESH_B200_H_
+#define ACTIONMESH_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMB_ABI_VERSION 3
+
+typedef void* amb_stream_t; /* cudaStream_t */
+
+/* ---- plumbing -------------------------------------------------------------------------------------------------- */
+const char* amb_last_error(void);
+int amb_abi_version(void);
+int amb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K9: CFG combine + Euler flow step + observed-frame mask ------------------------------------------------------
+ * Replaces actionmesh/scheduler/guidance.py:95-118 (aggregate_cfg) and actionmesh/scheduler/scheduler.py:238-248
+ * (flow step + masked in-place write, incl. the per-step `assert unobserved.any()` D2H sync, which is dropped).
+ *   v   = p[0] + sum_i scales[i] * (p[i+1] - p[i])               (fp32 arithmetic on bf16 predictions)
+ *   x_f = x_f + dt_signed * v      for every frame f with frame_update[f] != 0     (x fp32, in place)
+ * pred element (branch k, frame f, e) lives at pred + k*branch_stride + f*frame_stride + frame_offset + e.
+ */
+int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, const float* scales_host,
+                       float dt_signed, const uint8_t* frame_update, int n_frames, int64_t n_per_frame,
+                       int64_t branch_stride, int64_t frame_stride, int64_t frame_offset, amb_stream_t stream);
+
+/* ---- LayerNorm (affine, fp32 statistics) ---------------------------------------------------------------------------
+ * Replaces diffusers FP32LayerNorm at actionmesh/model/utils/block.py:64,83,98,107 and nn.LayerNorm at
+ * actionmesh/model/temporal_denoiser.py:108,239; also DinoV2's LayerNorms (transformers modeling_dinov2).
+ * x: (rows, cols) bf16 or fp32 (x_fp32), y: bf16.  cols must be a multiple of 256 and <= 4096.
+ */
+int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+                  int64_t ldy, int64_t rows, int cols, float eps, amb_stream_t stream);
+
+/* ---- small elementwise helpers -------------------------------------------------------------------------------------
+ * cast: fp32 -> bf16 (latents before proj_in, temporal_denoiser.py:205-206; context before to_k/to_v).
+ * timestep embedding: diffusers Timesteps(num_channels=C, flip_sin_to_cos=False, downscale_freq_shift=0) as used at
+ *   temporal_denoiser.py:57-61,213: out[r] = [sin(t_r*w_j) | cos(t_r*w_j)], w_j = exp(-ln(1e4) * j / (C/2)).
+ * add_bias_rows: y[r, :] += bias  (A.5: zero-context cross-attention collapses to to_out.0.bias, block.py:146).
+ */
+int amb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, amb_stream_t stream);
+int amb_timestep_embedding(const float* t, int rows, int channels, void* out_bf16, amb_stream_t stream);
+int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream);
+
+/* ---- tcgen05 GEMM with fused epilogues: C = epi(A · Wᵀ) ----------------------------------------------------------------
+ * Replaces every nn.Linear on the path (cuBLAS in the reference): proj_in/proj_out/time_proj
+ * (temporal_denoiser.py:206,213-214,242), linear_skip on cat[skip,h] without materialising the concat (block.py:131-133,
+ * a2/k_split), to_q/to_k/to_v with the head split, RMS qk-norm and RoPE of attention_processor.py:92-130 fused in the
+ * epilogue, to_out + residual (attention_processor.py:147, block.py:137,146), FeedForward GELU(erf) MLP (block.py:152).
+ * A:(m,k) bf16 row-major, W:(n,k) bf16 row-major (nn.Linear layout), fp32 accumulation in TMEM.
+ * k % 64 == 0, n % 64 == 0.
+ */
+typedef struct amb_gemm_args {
+  const void* a;        /* bf16 (m, k) */
+  int64_t lda;
+  const void* a2;       /* optional second A source supplying columns k >= k_split (NULL = unused) */
+  int64_t lda2;
+  int32_t k_split;      /* multiple of 64 */
+  const void* w;        /* bf16 (n, k) */
+  int64_t ldw;
+  void* c;              /* bf16 or fp32 (m', n) */
+  int64_t ldc;
+  int32_t c_fp32;
+  int32_t m, n, k;
+  const float* bias;    /* (n) or NULL */
+  const void* residual; /* (m', n) bf16/fp32 or NULL; added after the activation; may alias c */
+  int64_t ldr;
+  int32_t res_fp32;
+  int32_t act;          /* 0 none, 1 GELU(erf) */
+  const float* col_scale; /* (n) or NULL: per-column scale applied after bias/act, before residual (DinoV2 LayerScale) */
+  /* output row remap: dst_row = (row / grp_rows) * grp_stride + row % grp_rows + row_off  (grp_rows == 0: identity) */
+  int32_t grp_rows, grp_stride, row_off;
+  /* per-head (128 columns) RMSNorm for columns [0, norm_cols): weight norm_w0 for col < norm_seg, norm_w1 otherwise */
+  int32_t norm_cols, norm_seg;
+  const float* norm_w0;
+  const float* norm_w1;
+  float norm_eps;
+  /* interleaved-pair RoPE for columns [0, rope_cols): cos/sin tables (n_pos, 64) fp32, pos = row / rope_rows_per_pos */
+  int32_t rope_cols;
+  const float* rope_cos;
+  const float* rope_sin;
+  int32_t rope_rows_per_pos;
+} amb_gemm_args;
+
+int amb_gemm_bf16(const amb_gemm_args* args, amb_stream_t stream);
+
+/* ---- tcgen05 flash attention forward ------------------------------------------------------------------------------
+ * Replaces F.scaled_dot_product_attention at actionmesh/model/utils/attention_processor.py:133-139 (non-causal, no
+ * mask, dropout 0) for the inflated self-attention (S = T*(N+1)) and the per-frame cross-attention (S_k = 257), and
+ * DinoV2's attention (head_dim 64).  Strided 4-D views so q/k/v are read straight out of the fused QKV GEMM output and
+ * o is written in (b, s, h*d) order for to_out.  Strides in elements; the innermost (d) stride is 1.
+ * kv may be split in `kv_chunks` equal chunks of `sk_chunk` keys whose base pointers are k + c*k_chunk_stride (used by
+ * the frame-sharded window: chunk c is rank c's all-gathered K/V).  kv_chunks == 1 for the plain case.
+ */
+typedef struct amb_attn_args {
+  const void* q;
+  const void* k;
+  const void* v;
+  void* o;
+  int64_t q_stride_b, q_stride_h, q_stride_s;
+  int64_t k_stride_b, k_stride_h, k_stride_s;
+  int64_t v_stride_b, v_stride_h, v_stride_s;
+  int64_t o_stride_b, o_stride_h, o_stride_s;
+  int32_t batch, heads, sq, sk, head_dim;
+  float scale; /* softmax scale, 1/sqrt(head_dim) in the reference */
+  int32_t kv_chunks;
+  int32_t sk_chunk;
+  int64_t k_chunk_stride, v_chunk_stride;
+} amb_attn_args;
+
+int amb_flash_attn_fwd(const amb_attn_args* args, amb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACTIONMESH_B200_H_ */

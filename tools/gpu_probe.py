@@ -1,0 +1,359 @@
+"""Kernel bring-up probe (runs on the GPU box).  Each group runs in its own subprocess so a trapped kernel cannot
+poison the CUDA context of the next group.  Results -> gpurun_out/probe_<group>.json + stdout summary.
+
+    python tools/gpu_probe.py            # all groups
+    python tools/gpu_probe.py gemm attn  # selected groups
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def _err(a, b):
+    import torch
+    a = a.float()
+    b = b.float()
+    d = (a - b).abs()
+    return {"max_abs": float(d.max()), "mean_abs": float(d.mean()), "ref_absmax": float(b.abs().max()),
+            "rel_fro": float(d.norm() / (b.norm() + 1e-30)), "nan": bool(torch.isnan(a).any())}
+
+
+def _time(fn, iters=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def group_elementwise(res):
+    import torch
+    from actionmesh_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(0)
+    # --- K9
+    T, NPF = 16, 2048 * 64
+    lat = torch.randn(1, T, 2048, 64, generator=g).to(dev)
+    pred_full = torch.randn(2, T, 2049, 64, generator=g).to(dev).bfloat16()
+    upd = torch.ones(T, dtype=torch.uint8)
+    upd[0] = 0
+    upd[7] = 0
+    upd = upd.to(dev)
+    ref = lat.clone()
+    p = pred_full[:, :, 1:, :].float()
+    v = p[0] + 7.5 * (p[1] - p[0])
+    dt = 0.0113
+    refu = ref + dt * v[None]
+    mask = upd.bool()
+    ref[0, mask] = refu[0, mask]
+    x = lat.clone()
+    ops.cfg_euler_step(x, pred_full, [7.5], dt, upd, n_branches=2, branch_stride=T * 2049 * 64,
+                       frame_stride=2049 * 64, frame_offset=64, n_per_frame=NPF)
+    torch.cuda.synchronize()
+    res["k9"] = _err(x, ref)
+    res["k9"]["observed_bit_identical"] = bool(torch.equal(x[0, 0], lat[0, 0]) and torch.equal(x[0, 7], lat[0, 7]))
+    ms = _time(lambda: ops.cfg_euler_step(x, pred_full, [7.5], dt, upd, n_branches=2, branch_stride=T * 2049 * 64,
+                                          frame_stride=2049 * 64, frame_offset=64, n_per_frame=NPF), iters=20)
+    nb = int(mask.sum()) * NPF * 12
+    res["k9"]["ms"] = ms
+    res["k9"]["GBps"] = nb / ms / 1e6
+    # --- layernorm
+    for cols in (1024, 2048):
+        for dt_ in (torch.bfloat16, torch.float32):
+            xx = (torch.randn(1000, cols, generator=g) * 2 + 0.5).to(dev).to(dt_)
+            gm = torch.randn(cols, generator=g).to(dev)
+            bt = torch.randn(cols, generator=g).to(dev)
+            y = ops.layernorm(xx, gm, bt, 1e-5)
+            r = torch.nn.functional.layer_norm(xx.float(), (cols,), gm, bt, 1e-5)
+            res[f"ln_{cols}_{str(dt_)[6:]}"] = _err(y, r)
+    xx = torch.randn(65568, 2048, generator=g).to(dev).bfloat16()
+    gm = torch.ones(2048, device=dev)
+    bt = torch.zeros(2048, device=dev)
+    out = torch.empty_like(xx)
+    ms = _time(lambda: ops.layernorm(xx, gm, bt, 1e-5, out=out), iters=10)
+    res["ln_big"] = {"ms": ms, "GBps": xx.numel() * 4 / ms / 1e6}
+    # --- cast / timestep / bias rows
+    a = torch.randn(4099, generator=g).to(dev)
+    res["cast"] = _err(ops.cast_bf16(a), a.bfloat16())
+    t = torch.tensor([0.0, 8.9285717, 502.98, 1000.0], device=dev)
+    emb = ops.timestep_embedding(t, 2048)
+    half = 1024
+    w = torch.exp(-math.log(10000.0) * torch.arange(half, device=dev, dtype=torch.float32) / half)
+    e = t[:, None] * w[None]
+    res["timestep_emb"] = _err(emb, torch.cat([e.sin(), e.cos()], -1))
+    y = torch.randn(100, 2048, generator=g).to(dev).bfloat16()
+    b = torch.randn(2048, generator=g).to(dev)
+    r = (y.float() + b).bfloat16()
+    ops.add_bias_rows(y, b)
+    res["add_bias_rows"] = _err(y, r)
+
+
+def _gemm_case(res, name, m, n, k, *, bias=False, act=0, residual=False, a2=False, row_map=None, out_fp32=False,
+               res_fp32=False, col_scale=False, norm=None, timing=False, seed=1):
+    import torch
+    from actionmesh_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = (torch.randn(m, k, generator=g) * 0.5).to(dev).bfloat16()
+    W = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(dev).bfloat16()
+    kw = {}
+    ref = A.float() @ W.float().t()
+    if a2:
+        k1 = k // 2
+        A1 = A[:, :k1].contiguous()
+        A2 = A[:, k1:].contiguous()
+        kw["a2"] = A2
+        Ain = A1
+    else:
+        Ain = A
+    if norm is not None:
+        nc, seg, rc, rpp = norm
+        w0 = (torch.rand(128, generator=g) + 0.5).to(dev)
+        w1 = (torch.rand(128, generator=g) + 0.5).to(dev)
+        npos = (m + rpp - 1) // rpp
+        ang = torch.rand(npos, 64, generator=g) * 6.28
+        cos, sin = ang.cos().to(dev), ang.sin().to(dev)
+        kw["norm"] = dict(cols=nc, seg=seg, w0=w0, w1=w1, eps=1e-6, rope_cols=rc, cos=cos, sin=sin, rows_per_pos=rpp)
+        r = ref.clone()
+        for c0 in range(0, nc, 128):
+            h = r[:, c0:c0 + 128]
+            h = h * torch.rsqrt(h.pow(2).mean(-1, keepdim=True) + 1e-6) * (w0 if c0 < seg else w1)
+            if c0 < rc:
+                pos = torch.arange(m, device=dev) // rpp
+                cc = cos[pos].repeat_interleave(2, dim=1)
+                ss = sin[pos].repeat_interleave(2, dim=1)
+                x0, x1 = h.reshape(m, 64, 2).unbind(-1)
+                rot = torch.stack([-x1, x0], -1).reshape(m, 128)
+                h = h * cc + rot * ss
+            r[:, c0:c0 + 128] = h
+        ref = r
+    if bias:
+        bv = torch.randn(n, generator=g).to(dev)
+        kw["bias"] = bv
+        if norm is None:
+            ref = ref + bv
+        else:
+            ref[:, norm[0]:] += bv[norm[0]:]
+    if act:
+        kw["act"] = 1
+        ref = torch.nn.functional.gelu(ref)
+    if col_scale:
+        cs = torch.randn(n, generator=g).to(dev)
+        kw["col_scale"] = cs
+        ref = ref * cs
+    mo = m
+    if row_map is not None:
+        gr, gs, ro = row_map
+        mo = (m // gr) * gs + ro + gr
+        kw["row_map"] = row_map
+    out = torch.full((mo, n), 7.0, device=dev, dtype=torch.float32 if out_fp32 else torch.bfloat16)
+    if residual:
+        R = torch.randn(mo, n, generator=g).to(dev)
+        R = R if res_fp32 else R.bfloat16()
+        kw["residual"] = R
+    ops.gemm(Ain, W, out, **kw)
+    torch.cuda.synchronize()
+    if row_map is not None:
+        gr, gs, ro = row_map
+        rows = torch.arange(m, device=dev)
+        drow = (rows // gr) * gs + rows % gr + ro
+        full = torch.full((mo, n), 7.0, device=dev)
+        if residual:
+            full[drow] = ref + kw["residual"].float()[drow]
+        else:
+            full[drow] = ref
+        ref = full
+    elif residual:
+        ref = ref + kw["residual"].float()
+    res[name] = _err(out, ref)
+    if timing:
+        ms = _time(lambda: ops.gemm(Ain, W, out, **kw), iters=5)
+        res[name]["ms"] = ms
+        res[name]["TFLOPs"] = 2.0 * m * n * k / ms / 1e9
+
+
+def group_gemm(res):
+    _gemm_case(res, "g_basic_128x256x64", 128, 256, 64)
+    _gemm_case(res, "g_256x256x128", 256, 256, 128)
+    _gemm_case(res, "g_n128_tail_m300", 300, 128, 192)
+    _gemm_case(res, "g_n64", 200, 64, 128, bias=True, out_fp32=True)
+    _gemm_case(res, "g_multi_tile_persist", 128 * 40, 2048, 256)   # > 148 tiles => several tiles per CTA
+    _gemm_case(res, "g_bias_gelu_res", 512, 512, 256, bias=True, act=1, residual=True)
+    _gemm_case(res, "g_a2_split", 384, 256, 512, a2=True, bias=True)
+    _gemm_case(res, "g_rowmap", 256, 256, 64, bias=True, row_map=(64, 65, 1))
+    _gemm_case(res, "g_fp32_res_colscale", 257, 256, 128, bias=True, residual=True, res_fp32=True, out_fp32=True, col_scale=True)
+    _gemm_case(res, "g_norm_rope_qkv", 300, 768, 256, norm=(512, 256, 512, 100))
+    _gemm_case(res, "g_norm_only_q", 300, 256, 256, norm=(256, 256, 0, 1))
+    _gemm_case(res, "g_norm_kv_bias", 300, 512, 128, norm=(256, 256, 0, 1), bias=True)
+
+
+def group_gemm_perf(res):
+    _gemm_case(res, "p_8192x2048x2048", 8192, 2048, 2048, timing=True)
+    _gemm_case(res, "p_65568x2048x2048_res", 65568, 2048, 2048, bias=True, residual=True, timing=True)
+    _gemm_case(res, "p_65568x8192x2048_gelu", 65568, 8192, 2048, bias=True, act=1, timing=True)
+    _gemm_case(res, "p_65568x2048x8192_res", 65568, 2048, 8192, bias=True, residual=True, timing=True)
+    _gemm_case(res, "p_65568x6144x2048_qkv", 65568, 6144, 2048, norm=(4096, 2048, 4096, 2049), timing=True)
+    _gemm_case(res, "p_65568x2048x4096_skip", 65568, 2048, 4096, a2=True, bias=True, timing=True)
+    import torch
+    # cuBLAS reference point for the same shape (baseline only)
+    a = torch.randn(65568, 2048, device="cuda").bfloat16()
+    w = torch.randn(2048, 2048, device="cuda").bfloat16()
+    ms = _time(lambda: torch.matmul(a, w.t()), iters=5)
+    res["cublas_65568x2048x2048"] = {"ms": ms, "TFLOPs": 2.0 * 65568 * 2048 * 2048 / ms / 1e9}
+
+
+def _attn_ref(q, k, v, scale):
+    import torch
+    # q:(B,Sq,H,D)
+    qf, kf, vf = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) * scale
+    p = s.softmax(-1)
+    return (p @ vf).permute(0, 2, 1, 3)
+
+
+def _attn_case(res, name, B, H, Sq, Sk, D, *, mode="rand", fused=False, timing=False, seed=3, kv_chunks=1):
+    import torch
+    from actionmesh_b200 import ops
+    dev = "cuda"
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    scale = 1.0 / math.sqrt(D)
+    if fused:
+        assert Sq == Sk
+        buf = torch.randn(B, Sq, 3 * H * D, generator=g).to(dev).bfloat16()
+        q = buf[:, :, 0 * H * D:1 * H * D].view(B, Sq, H, D)
+        k = buf[:, :, 1 * H * D:2 * H * D].view(B, Sq, H, D)
+        v = buf[:, :, 2 * H * D:3 * H * D].view(B, Sq, H, D)
+    else:
+        q = torch.randn(B, Sq, H, D, generator=g).to(dev).bfloat16()
+        k = torch.randn(B, Sk, H, D, generator=g).to(dev).bfloat16()
+        v = torch.randn(B, Sk, H, D, generator=g).to(dev).bfloat16()
+    if mode == "vones":
+        v = torch.ones_like(v)
+    elif mode == "kzero":
+        k = torch.zeros_like(k)
+    elif mode == "sharp":
+        q = q * 4
+    out = torch.full((B, Sq, H, D), 3.0, device=dev, dtype=torch.bfloat16)
+    if kv_chunks > 1:
+        kc = k.view(B, kv_chunks, Sk // kv_chunks, H, D)
+        vc = v.view(B, kv_chunks, Sk // kv_chunks, H, D)
+        ops.flash_attn(q, kc, vc, out, scale, kv_chunks=kv_chunks)
+    else:
+        ops.flash_attn(q, k, v, out, scale)
+    torch.cuda.synchronize()
+    if Sq * Sk * B * H <= 2 ** 31:
+        ref = _attn_ref(q, k, v, scale)
+    else:
+        ref = torch.nn.functional.scaled_dot_product_attention(
+            q.permute(0, 2, 1, 3), k.permute(0, 2, 1, 3), v.permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    res[name] = _err(out, ref)
+    if timing:
+        if kv_chunks > 1:
+            fn = lambda: ops.flash_attn(q, kc, vc, out, scale, kv_chunks=kv_chunks)
+        else:
+            fn = lambda: ops.flash_attn(q, k, v, out, scale)
+        ms = _time(fn, iters=3, warm=1)
+        res[name]["ms"] = ms
+        res[name]["TFLOPs"] = 4.0 * B * H * Sq * Sk * D / ms / 1e9
+
+
+def group_attn(res):
+    _attn_case(res, "a_1tile_vones", 1, 1, 256, 64, 128, mode="vones")
+    _attn_case(res, "a_1tile_kzero", 1, 1, 256, 64, 128, mode="kzero")
+    _attn_case(res, "a_1tile_rand", 1, 1, 256, 64, 128)
+    _attn_case(res, "a_2tiles", 1, 1, 256, 128, 128)
+    _attn_case(res, "a_5tiles_stagewrap", 1, 2, 256, 320, 128)
+    _attn_case(res, "a_tails_q300_k257", 2, 2, 300, 257, 128)
+    _attn_case(res, "a_sharp_rescale", 1, 2, 512, 1024, 128, mode="sharp")
+    _attn_case(res, "a_fused_qkv_strided", 2, 4, 520, 520, 128, fused=True)
+    _attn_case(res, "a_chunks2", 2, 2, 256, 2 * 200, 128, kv_chunks=2)
+    _attn_case(res, "a_d64_s257", 3, 4, 257, 257, 64)
+    _attn_case(res, "a_d64_fused", 2, 16, 257, 257, 64, fused=True)
+
+
+def group_attn_perf(res):
+    _attn_case(res, "ap_s4098", 1, 16, 4098, 4098, 128, timing=True)
+    _attn_case(res, "ap_cross_2049x257", 16, 16, 2049, 257, 128, timing=True)
+    _attn_case(res, "ap_s32784_full", 2, 16, 32784, 32784, 128, fused=True, timing=True)
+    import torch
+    q = torch.randn(2, 16, 32784, 128, device="cuda").bfloat16()
+    ms = _time(lambda: torch.nn.functional.scaled_dot_product_attention(q, q, q), iters=2, warm=1)
+    res["torch_sdpa_s32784"] = {"ms": ms, "TFLOPs": 4.0 * 2 * 16 * 32784 * 32784 * 128 / ms / 1e9}
+
+
+GROUPS = {
+    "elementwise": group_elementwise, "gemm": group_gemm, "attn": group_attn,
+    "gemm_perf": group_gemm_perf, "attn_perf": group_attn_perf,
+}
+
+
+def run_group(name):
+    import torch
+    res = {}
+    t0 = time.time()
+    try:
+        GROUPS[name](res)
+        torch.cuda.synchronize()
+        res["_status"] = "ok"
+    except Exception as e:  # noqa: BLE001
+        res["_status"] = "EXC: " + repr(e)[:400]
+        res["_trace"] = traceback.format_exc()[-1500:]
+    res["_sec"] = time.time() - t0
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, f"probe_{name}.json"), "w") as f:
+        json.dump(res, f, indent=1)
+    return res
+
+
+def main():
+    args = sys.argv[1:]
+    if args and args[0] == "--child":
+        run_group(args[1])
+        return
+    names = args or list(GROUPS)
+    for n in names:
+        t0 = time.time()
+        try:
+            pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n], capture_output=True, text=True,
+                                timeout=420)
+            tail = (pr.stdout + pr.stderr)[-1200:]
+        except subprocess.TimeoutExpired:
+            tail = "TIMEOUT"
+        path = os.path.join(OUT, f"probe_{n}.json")
+        print(f"==== {n} ({time.time() - t0:.0f}s)")
+        if os.path.exists(path):
+            r = json.load(open(path))
+            for k, v in r.items():
+                if k.startswith("_trace"):
+                    continue
+                if isinstance(v, dict):
+                    s = " ".join(f"{a}={b:.4g}" if isinstance(b, float) else f"{a}={b}" for a, b in v.items())
+                else:
+                    s = str(v)
+                print(f"  {k}: {s}")
+            if r.get("_status") != "ok":
+                print(r.get("_trace", ""))
+                print("  child tail:", tail[-600:])
+        else:
+            print("  NO RESULT FILE; child tail:", tail)
+
+
+if __name__ == "__main__":
+    main()
