@@ -182,7 +182,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // K-major operand tile staged by TMA with SWIZZLE_128B: rows of 128 B (64 bf16), 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
-  return make_smem_desc(saddr, 0, 1024, 2);
+  return make_smem_desc(saddr, 16, 1024, 2);  // LBO is "1" (16 B) for swizzled K-major, as CUTLASS encodes it
 }
 // MN-major operand ([K rows][64 MN elems] boxes of 128 B rows): 8 K-rows = 1024 B (SBO); next 64 MN elems at lbo.
 __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr, uint32_t lbo_bytes) {
