@@ -141,11 +141,13 @@ __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restr
 }
 
 // diffusers Timesteps(flip_sin_to_cos=False, downscale_freq_shift=0): [sin(t w_j) | cos(t w_j)], w_j = exp(-ln(1e4) j / half)
-__global__ void timestep_embedding_kernel(const float* __restrict__ t, int rows, int channels,
-                                          __nv_bfloat16* __restrict__ out) {
+// Row r uses t[r % n_t] * (1 - mask[r]): temporal_denoiser.py:209-212 (`diffusion_time.repeat(T) * (1 - mask)`, observed
+// frames are conditioned on t = 0).
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int n_t, const float* __restrict__ mask, int rows,
+                                          int channels, __nv_bfloat16* __restrict__ out) {
   const int half = channels >> 1;
   const int r = blockIdx.x;
-  const float tv = t[r];
+  const float tv = t[r % n_t] * (mask ? (1.0f - mask[r]) : 1.0f);
   for (int j = threadIdx.x; j < half; j += blockDim.x) {
     const float w = expf(-9.210340371976184f * (float)j / (float)half);
     const float a = tv * w;
@@ -254,11 +256,12 @@ int amb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, amb_stream_t 
   return AMB_OK;
 }
 
-int amb_timestep_embedding(const float* t, int rows, int channels, void* out_bf16, amb_stream_t stream) {
-  AMB_CHECK_ARG(t && out_bf16, "timestep_embedding: null pointer");
+int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows, int channels, void* out_bf16,
+                           amb_stream_t stream) {
+  AMB_CHECK_ARG(t && out_bf16 && n_t > 0, "timestep_embedding: null pointer");
   AMB_CHECK_ARG(channels % 2 == 0 && channels > 0, "timestep_embedding: channels must be even");
   if (rows <= 0) return AMB_OK;
-  timestep_embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(t, rows, channels, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  timestep_embedding_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>(t, n_t, mask, rows, channels, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -1,0 +1,395 @@
+"""B200Denoiser — sm_100a implementation of ActionMesh's temporal 3D DiT denoiser behind the reference's duck type.
+
+Mirrors `ActionMeshDenoiser` (reference actionmesh/model/temporal_denoiser.py:23-249): same constructor fields, same
+state-dict keys, same `forward(hidden_states, context, framestep, diffusion_time, mask, freqs_rot)` ->
+`(out (B,T,N,C), freqs_rot)` contract that `SchedulerFlow._diffusion_forward` calls (scheduler.py:151-158), plus
+`.device / .eval() / .to() / from_pretrained()` used by the pipeline (pipeline.py:171-184).
+
+All arithmetic runs in hand-written CUDA kernels through the C ABI (actionmesh_b200.ops); torch only owns the device
+buffers.  Layout in HBM (default config, B=2 CFG branches, T=16, L=N+1=2049, D=2048, M=B*T*L=65 568 token rows):
+    h      (M, D)   bf16  residual stream, rows ordered (b, t, l); row l=0 of every frame is the time token
+    xn     (M, D)   bf16  LayerNorm output feeding the next GEMM
+    qkv    (M, 3D)  bf16  fused [Q|K|V] with standard head order (weights are re-packed once)
+    att    (M, D)   bf16  attention output in (b, s, h, d) order == row-major (M, D)
+    ff     (M, F)   bf16  GELU(MLP1)
+    skips  10 x (M, D) bf16 U-ViT long-skip stack
+The per-window `WindowState` returned in place of `freqs_rot` carries the RoPE tables AND the step-invariant context
+K/V of all 21 cross-attention layers, exactly the role the reference gives `freqs_rot` (an opaque cache the
+scheduler threads through its loop, scheduler.py:204,224-232).
+"""
+from __future__ import annotations
+
+import json
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import AmbError
+
+
+@dataclass
+class DenoiserConfig:
+    """Same fields/defaults as ActionMeshDenoiser's dataclass (temporal_denoiser.py:29-49)."""
+    num_tokens_nominal: int = 2048
+    temporal_context_size: int = 16
+    in_channels: int = 64
+    num_layers: int = 21
+    num_attention_heads: int = 16
+    width: int = 2048
+    mlp_ratio: float = 4.0
+    cross_attention_dim: int = 1024
+    inflated_layers: tuple = field(default_factory=lambda: tuple(range(21)))
+
+    @property
+    def head_dim(self) -> int:
+        return self.width // self.num_attention_heads
+
+    @property
+    def ff_dim(self) -> int:
+        return int(self.width * self.mlp_ratio)
+
+
+def repack_self_qkv(wq: torch.Tensor, wk: torch.Tensor, wv: torch.Tensor, heads: int) -> torch.Tensor:
+    """Head-interleaved split of attention_processor.py:106-110 folded into the weights.
+
+    The reference takes head h's q/k/v from columns [3dh, 3d(h+1)) of cat(q,k,v).  Selecting the matching ROWS of
+    cat(Wq,Wk,Wv) once gives a standard fused QKV GEMM whose output is [Q(h,d) | K(h,d) | V(h,d)]."""
+    wcat = torch.cat([wq, wk, wv], dim=0)  # (3*inner, in)
+    inner = wq.shape[0]
+    dh = inner // heads
+    wcat = wcat.view(heads, 3, dh, -1)
+    return torch.cat([wcat[:, 0].reshape(inner, -1), wcat[:, 1].reshape(inner, -1), wcat[:, 2].reshape(inner, -1)], 0)
+
+
+def repack_cross_kv(wk: torch.Tensor, wv: torch.Tensor, heads: int) -> torch.Tensor:
+    """Same for the cross-attention [k|v] split (attention_processor.py:111-115); q keeps the plain head view (:117)."""
+    wcat = torch.cat([wk, wv], dim=0)
+    inner = wk.shape[0]
+    dh = inner // heads
+    wcat = wcat.view(heads, 2, dh, -1)
+    return torch.cat([wcat[:, 0].reshape(inner, -1), wcat[:, 1].reshape(inner, -1)], 0)
+
+
+class WindowState:
+    """Opaque per-window cache returned in the `freqs_rot` slot: RoPE tables + context K/V of every layer."""
+
+    def __init__(self):
+        self.rope_cos: Optional[torch.Tensor] = None   # (B*T, d_h/2) fp32
+        self.rope_sin: Optional[torch.Tensor] = None
+        self.ctx_kv: list[Optional[torch.Tensor]] = []  # per layer (B*T*S_ctx, 2*D) bf16, [K normed | V]
+        self.ctx_zero: list[bool] = []                  # per batch element: context identically zero (A.5)
+        self.shape = None
+
+
+class B200Denoiser:
+    """Drop-in for ActionMeshDenoiser on the Stage-I hot path (inference only)."""
+
+    def __init__(self, config: Optional[DenoiserConfig] = None, **kwargs):
+        self.config = config if config is not None else DenoiserConfig(**kwargs)
+        c = self.config
+        if c.head_dim != 128:
+            raise AmbError(f"B200Denoiser: head_dim must be 128 (width {c.width} / heads {c.num_attention_heads})")
+        if c.width % 256 or c.in_channels % 64 or c.cross_attention_dim % 64:
+            raise AmbError("B200Denoiser: width must be a multiple of 256, in_channels/cross_attention_dim of 64")
+        self.out_channels = c.in_channels
+        self._device = torch.device("cpu")
+        self._w: dict = {}          # packed device weights
+        self._ws: dict = {}         # workspaces keyed by (B, T, N)
+        self._loaded = False
+
+    # ------------------------------------------------------------------ nn.Module-like surface used by the pipeline
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise AmbError("B200Denoiser runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        if self._loaded and self._device != device:
+            self._w = {k: v.to(device) for k, v in self._w.items()}
+            self._ws = {}
+        self._device = device
+        return self
+
+    @classmethod
+    def from_pretrained(cls, path: str, device="cuda") -> "B200Denoiser":
+        """Mirror of PyTorchModelHubMixin.from_pretrained(f"{dir}/denoiser") (pipeline.py:180-182): config.json +
+        model.safetensors / pytorch_model.bin with the reference's state-dict keys."""
+        cfg_path = os.path.join(path, "config.json")
+        kwargs = {}
+        if os.path.exists(cfg_path):
+            raw = json.load(open(cfg_path))
+            fields = DenoiserConfig.__dataclass_fields__
+            kwargs = {k: (tuple(v) if isinstance(v, list) else v) for k, v in raw.items() if k in fields}
+        model = cls(DenoiserConfig(**kwargs))
+        st = os.path.join(path, "model.safetensors")
+        if os.path.exists(st):
+            from safetensors.torch import load_file
+            sd = load_file(st)
+        else:
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        model.to(device)
+        model.load_state_dict(sd)
+        return model
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, sd: dict) -> None:
+        """Pack the reference's state dict (keys of SURVEY A.1) into kernel-ready device tensors: GEMM weights bf16
+        (QKV / KV fused and head-permuted), biases / norm weights fp32."""
+        c = self.config
+        dev = self._device
+        if dev.type != "cuda":
+            raise AmbError("call .to('cuda') before load_state_dict")
+        H = c.num_attention_heads
+
+        def W(name):  # GEMM operand
+            return sd[name].detach().to(device=dev, dtype=torch.float32).to(torch.bfloat16).contiguous()
+
+        def V(name):  # fp32 vector
+            return sd[name].detach().to(device=dev, dtype=torch.float32).contiguous()
+
+        w = {}
+        w["proj_in.w"], w["proj_in.b"] = W("proj_in.weight"), V("proj_in.bias")
+        w["time1.w"], w["time1.b"] = W("time_proj.linear_1.weight"), V("time_proj.linear_1.bias")
+        w["time2.w"], w["time2.b"] = W("time_proj.linear_2.weight"), V("time_proj.linear_2.bias")
+        w["norm_out.g"], w["norm_out.b"] = V("norm_out.weight"), V("norm_out.bias")
+        w["proj_out.w"], w["proj_out.b"] = W("proj_out.weight"), V("proj_out.bias")
+        for i in range(c.num_layers):
+            p = f"blocks.{i}."
+            if i > c.num_layers // 2:
+                w[p + "skip.w"], w[p + "skip.b"] = W(p + "linear_skip.weight"), V(p + "linear_skip.bias")
+                w[p + "norm_skip.g"], w[p + "norm_skip.b"] = V(p + "norm_skip.weight"), V(p + "norm_skip.bias")
+            for n in ("norm_s_attn", "norm_x_attn", "norm_ff"):
+                w[p + n + ".g"], w[p + n + ".b"] = V(p + n + ".weight"), V(p + n + ".bias")
+            f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
+            w[p + "s.qkv"] = repack_self_qkv(f32(p + "s_attn.to_q.weight"), f32(p + "s_attn.to_k.weight"),
+                                             f32(p + "s_attn.to_v.weight"), H).to(torch.bfloat16).contiguous()
+            w[p + "s.nq"], w[p + "s.nk"] = V(p + "s_attn.norm_q.weight"), V(p + "s_attn.norm_k.weight")
+            w[p + "s.o.w"], w[p + "s.o.b"] = W(p + "s_attn.to_out.0.weight"), V(p + "s_attn.to_out.0.bias")
+            w[p + "x.q"] = W(p + "x_attn.to_q.weight")
+            w[p + "x.kv"] = repack_cross_kv(f32(p + "x_attn.to_k.weight"), f32(p + "x_attn.to_v.weight"),
+                                            H).to(torch.bfloat16).contiguous()
+            w[p + "x.nq"], w[p + "x.nk"] = V(p + "x_attn.norm_q.weight"), V(p + "x_attn.norm_k.weight")
+            w[p + "x.o.w"], w[p + "x.o.b"] = W(p + "x_attn.to_out.0.weight"), V(p + "x_attn.to_out.0.bias")
+            w[p + "ff1.w"], w[p + "ff1.b"] = W(p + "ff.net.0.proj.weight"), V(p + "ff.net.0.proj.bias")
+            w[p + "ff2.w"], w[p + "ff2.b"] = W(p + "ff.net.2.weight"), V(p + "ff.net.2.bias")
+        self._w = w
+        self._loaded = True
+
+    def init_random_(self, seed: int = 1234, residual_scale: Optional[float] = None) -> None:
+        """Synthetic weights for benchmarks (no checkpoints offline): torch default Linear/LayerNorm inits, residual
+        branch output projections scaled by 1/sqrt(num_layers) so activations stay O(1).  Generated
+        directly on the GPU (no 5.8 GB host copy)."""
+        c = self.config
+        g = torch.Generator(device=self._device).manual_seed(seed)
+        rs = residual_scale if residual_scale is not None else 1.0 / math.sqrt(c.num_layers)
+
+        def lin(out_f, in_f, scale=1.0, bias=True):
+            bound = 1.0 / math.sqrt(in_f)
+            wt = (torch.rand(out_f, in_f, generator=g, device=self._device) * 2 - 1) * bound * scale
+            bs = (torch.rand(out_f, generator=g, device=self._device) * 2 - 1) * bound * scale if bias else None
+            return wt, bs
+
+        sd = {}
+        sd["proj_in.weight"], sd["proj_in.bias"] = lin(c.width, c.in_channels)
+        sd["time_proj.linear_1.weight"], sd["time_proj.linear_1.bias"] = lin(c.width * 4, c.width)
+        sd["time_proj.linear_2.weight"], sd["time_proj.linear_2.bias"] = lin(c.width, c.width * 4)
+        sd["norm_out.weight"] = torch.ones(c.width, device=self._device)
+        sd["norm_out.bias"] = torch.zeros(c.width, device=self._device)
+        sd["proj_out.weight"], sd["proj_out.bias"] = lin(c.in_channels, c.width)
+        for i in range(c.num_layers):
+            p = f"blocks.{i}."
+            b = {}
+            if i > c.num_layers // 2:
+                b[p + "linear_skip.weight"], b[p + "linear_skip.bias"] = lin(c.width, 2 * c.width)
+                b[p + "norm_skip.weight"] = torch.ones(c.width, device=self._device)
+                b[p + "norm_skip.bias"] = torch.zeros(c.width, device=self._device)
+            for n in ("norm_s_attn", "norm_x_attn", "norm_ff"):
+                b[p + n + ".weight"] = torch.ones(c.width, device=self._device)
+                b[p + n + ".bias"] = torch.zeros(c.width, device=self._device)
+            for a, kd in (("s_attn", c.width), ("x_attn", c.cross_attention_dim)):
+                b[p + a + ".to_q.weight"], _ = lin(c.width, c.width, bias=False)
+                b[p + a + ".to_k.weight"], _ = lin(c.width, kd, bias=False)
+                b[p + a + ".to_v.weight"], _ = lin(c.width, kd, bias=False)
+                b[p + a + ".norm_q.weight"] = torch.ones(c.head_dim, device=self._device)
+                b[p + a + ".norm_k.weight"] = torch.ones(c.head_dim, device=self._device)
+                b[p + a + ".to_out.0.weight"], b[p + a + ".to_out.0.bias"] = lin(c.width, c.width, scale=rs)
+            b[p + "ff.net.0.proj.weight"], b[p + "ff.net.0.proj.bias"] = lin(c.ff_dim, c.width)
+            b[p + "ff.net.2.weight"], b[p + "ff.net.2.bias"] = lin(c.width, c.ff_dim, scale=rs)
+            sd.update(b)
+        self.load_state_dict(sd)
+        del sd
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B: int, T: int, N: int) -> dict:
+        key = (B, T, N)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        c = self.config
+        dev = self._device
+        L = N + 1
+        M = B * T * L
+        bf = torch.bfloat16
+        n_skips = c.num_layers // 2
+        ws = {
+            "x_in": torch.empty(B * T * N, c.in_channels, dtype=bf, device=dev),
+            "t_emb": torch.empty(B * T, c.width, dtype=bf, device=dev),
+            "t_hid": torch.empty(B * T, c.width * 4, dtype=bf, device=dev),
+            "h": torch.empty(M, c.width, dtype=bf, device=dev),
+            "xn": torch.empty(M, c.width, dtype=bf, device=dev),
+            "tmp": torch.empty(M, c.width, dtype=bf, device=dev),
+            "qkv": torch.empty(M, 3 * c.width, dtype=bf, device=dev),
+            "att": torch.empty(M, c.width, dtype=bf, device=dev),
+            "ff": torch.empty(M, c.ff_dim, dtype=bf, device=dev),
+            "skips": [torch.empty(M, c.width, dtype=bf, device=dev) for _ in range(n_skips)],
+            "pred": torch.empty(M, c.in_channels, dtype=bf, device=dev),
+        }
+        self._ws = {key: ws}  # keep one shape resident
+        return ws
+
+    # ------------------------------------------------------------------ per-window cache
+    def precompute_window(self, context: torch.Tensor, framestep: torch.Tensor, N: int) -> WindowState:
+        """Step-invariant work of one AR window: RoPE tables (temporal_denoiser.py:114-149) and, for every layer,
+        K = norm_k(to_k(ctx)), V = to_v(ctx) of the cross-attention (attention_processor.py:101-124).  Batch elements
+        whose context is identically zero (the CFG "no image" branch, guidance.py:73) are flagged so their
+        cross-attention collapses to `to_out.0.bias`; that check is the only host sync, once per window."""
+        c = self.config
+        dev = self._device
+        B, T, S, Dc = context.shape
+        st = WindowState()
+        st.shape = (B, T, N)
+        # RoPE: theta_j = 10000^(-2j/d_h); phase = (framestep - min) * theta_j   (rotary_embedding.py:42-58)
+        fs = framestep.detach().to("cpu", torch.float32)
+        pos = (fs - fs.min(dim=1, keepdim=True).values).reshape(B * T)
+        inv = 1.0 / (10000.0 ** (torch.arange(0, c.head_dim, 2, dtype=torch.float32) / c.head_dim))
+        ph = torch.outer(pos, inv)
+        st.rope_cos = ph.cos().to(dev).contiguous()
+        st.rope_sin = ph.sin().to(dev).contiguous()
+        ctx = context.detach().to(device=dev, dtype=torch.float32).contiguous()
+        st.ctx_zero = [bool(z) for z in (ctx.reshape(B, -1).abs().amax(dim=1) == 0).tolist()]
+        ctx_bf = ops.cast_bf16(ctx.view(B * T * S, Dc))
+        for i in range(c.num_layers):
+            p = f"blocks.{i}."
+            kv = torch.empty(B * T * S, 2 * c.width, dtype=torch.bfloat16, device=dev)
+            ops.gemm(ctx_bf, self._w[p + "x.kv"], kv,
+                     norm=dict(cols=c.width, seg=c.width, w0=self._w[p + "x.nk"], eps=1e-6))
+            st.ctx_kv.append(kv)
+        return st
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, context: torch.Tensor, framestep: torch.Tensor,
+                diffusion_time: torch.Tensor, mask: Optional[torch.Tensor] = None, freqs_rot=None):
+        """ActionMeshDenoiser.forward (temporal_denoiser.py:151-249).  Returns (prediction (B,T,N,C) bf16 view, state).
+
+        `freqs_rot` is the WindowState from a previous call of the same window (or None)."""
+        if not self._loaded:
+            raise AmbError("B200Denoiser: weights not loaded")
+        B, T, N, C = hidden_states.shape
+        st = freqs_rot if isinstance(freqs_rot, WindowState) else None
+        if st is None or st.shape != (B, T, N):
+            st = self.precompute_window(context, framestep, N)
+        x32 = hidden_states.detach().to(device=self._device, dtype=torch.float32).contiguous()
+        t32 = diffusion_time.detach().to(device=self._device, dtype=torch.float32).contiguous()
+        m32 = None
+        if mask is not None:
+            m32 = mask.detach().to(device=self._device, dtype=torch.float32).reshape(B * T).contiguous()
+        ws = self._workspace(B, T, N)
+        ops.cast_bf16(x32.view(B * T * N, C), out=ws["x_in"])
+        pred = self._forward_packed(ws, st, B, T, N, t32, m32, n_input_branches=B)
+        return pred.view(B, T, N + 1, C)[:, :, 1:, :], st
+
+    __call__ = forward
+
+    def _forward_packed(self, ws: dict, st: WindowState, B: int, T: int, N: int, t32: torch.Tensor,
+                        m32: Optional[torch.Tensor], n_input_branches: int) -> torch.Tensor:
+        """Runs the 21-block DiT on ws['x_in'] (bf16 latents of `n_input_branches` batch elements; when fewer than B,
+        the same latents feed every CFG branch) and leaves the prediction in ws['pred'] (M, C) bf16."""
+        c = self.config
+        w = self._w
+        D, H, dh = c.width, c.num_attention_heads, c.head_dim
+        L = N + 1
+        M = B * T * L
+        h, xn, tmp, qkv, att, ff = ws["h"], ws["xn"], ws["tmp"], ws["qkv"], ws["att"], ws["ff"]
+        scale = 1.0 / math.sqrt(dh)
+
+        # proj_in (temporal_denoiser.py:205-206): rows (bt, n) -> h rows (bt, 1 + n).  When the CFG branches share
+        # their latents (guidance.py:56 `cat([latent] * K)`) the same bf16 rows feed every branch's copy.
+        nb = n_input_branches
+        x_in = ws["x_in"][: nb * T * N]
+        for r in range(B // nb):
+            ops.gemm(x_in, w["proj_in.w"], h[r * nb * T * L:], bias=w["proj_in.b"], row_map=(N, L, 1))
+        # time token (temporal_denoiser.py:209-217)
+        ops.timestep_embedding(t32, D, out=ws["t_emb"], mask=m32, rows=B * T)
+        ops.gemm(ws["t_emb"], w["time1.w"], ws["t_hid"], bias=w["time1.b"], act=1)
+        ops.gemm(ws["t_hid"], w["time2.w"], h, bias=w["time2.b"], row_map=(1, L, 0))
+
+        # U-ViT long skips (temporal_denoiser.py:222-232) without copies: a pushing block writes its output straight
+        # into a skip buffer, which then serves as the (read-only) residual input of the next block; the next block's
+        # first residual GEMM writes into the work buffer `h` again.
+        skips = ws["skips"]
+        sp = 0
+        half = c.num_layers // 2
+        h_in = h  # where the current residual stream lives
+        for i in range(c.num_layers):
+            p = f"blocks.{i}."
+            if i > half:  # block.py:131-133: LN(W_skip [skip | h] + b) without materialising the concat
+                sp -= 1
+                ops.gemm(skips[sp], w[p + "skip.w"], tmp, a2=h_in, bias=w[p + "skip.b"])
+                ops.layernorm(tmp, w[p + "norm_skip.g"], w[p + "norm_skip.b"], 1e-5, out=h)
+                h_in = h
+            # ---- self-attention (block.py:137-142, attention_processor.py:49-166)
+            ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
+            ops.gemm(xn, w[p + "s.qkv"], qkv,
+                     norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
+                               cos=st.rope_cos, sin=st.rope_sin, rows_per_pos=L))
+            if i in c.inflated_layers:
+                view = (B, T * L, H, dh)
+            else:
+                view = (B * T, L, H, dh)
+            q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            ops.flash_attn(q4, k4, v4, att.view(*view), scale)
+            ops.gemm(att, w[p + "s.o.w"], h, bias=w[p + "s.o.b"], residual=h_in)
+            h_in = h
+            # ---- cross-attention (block.py:146-149); zero-context batch elements reduce to + to_out.0.bias (A.5)
+            TL = T * L
+            S = st.ctx_kv[i].shape[0] // (B * T)
+            for b in range(B):
+                rows = slice(b * TL, (b + 1) * TL)
+                if st.ctx_zero[b]:
+                    ops.add_bias_rows(h[rows], w[p + "x.o.b"])
+                    continue
+                ops.layernorm(h[rows], w[p + "norm_x_attn.g"], w[p + "norm_x_attn.b"], 1e-5, out=xn[rows])
+                qb = qkv[rows, 0:D]
+                ops.gemm(xn[rows], w[p + "x.q"], qb, norm=dict(cols=D, seg=D, w0=w[p + "x.nq"], eps=1e-6))
+                kvb = st.ctx_kv[i][b * T * S:(b + 1) * T * S]
+                ops.flash_attn(qb.view(T, L, H, dh), kvb[:, 0:D].view(T, S, H, dh), kvb[:, D:2 * D].view(T, S, H, dh),
+                               att[rows].view(T, L, H, dh), scale)
+                ops.gemm(att[rows], w[p + "x.o.w"], h[rows], bias=w[p + "x.o.b"], residual=h[rows])
+            # ---- feed-forward (block.py:152)
+            ops.layernorm(h, w[p + "norm_ff.g"], w[p + "norm_ff.b"], 1e-5, out=xn)
+            ops.gemm(xn, w[p + "ff1.w"], ff, bias=w[p + "ff1.b"], act=1)
+            if i < half:  # temporal_denoiser.py:231-232: push == write the block output into the skip buffer
+                ops.gemm(ff, w[p + "ff2.w"], skips[sp], bias=w[p + "ff2.b"], residual=h)
+                h_in = skips[sp]
+                sp += 1
+            else:
+                ops.gemm(ff, w[p + "ff2.w"], h, bias=w[p + "ff2.b"], residual=h)
+        # output head (temporal_denoiser.py:239-242); the time-token rows are computed and ignored by the consumers
+        ops.layernorm(h_in, w["norm_out.g"], w["norm_out.b"], 1e-5, out=xn)
+        ops.gemm(xn, w["proj_out.w"], ws["pred"], bias=w["proj_out.b"])
+        return ws["pred"]

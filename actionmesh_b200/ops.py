@@ -82,13 +82,19 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
-def timestep_embedding(t: torch.Tensor, channels: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def timestep_embedding(t: torch.Tensor, channels: int, out: Optional[torch.Tensor] = None, *,
+                       mask: Optional[torch.Tensor] = None, rows: Optional[int] = None) -> torch.Tensor:
+    """Row r: sinusoidal embedding of t[r % len(t)] * (1 - mask[r]) (temporal_denoiser.py:209-213)."""
     global launch_count
     _need(t, torch.float32, "t")
-    rows = t.numel()
+    if mask is not None:
+        _need(mask, torch.float32, "mask")
+        rows = mask.numel()
+    if rows is None:
+        rows = t.numel()
     if out is None:
         out = torch.empty((rows, channels), dtype=torch.bfloat16, device=t.device)
-    rc = _lib.load_library().amb_timestep_embedding(t.data_ptr(), rows, channels, out.data_ptr(), _stream())
+    rc = _lib.load_library().amb_timestep_embedding(t.data_ptr(), t.numel(), _ptr(mask), rows, channels, out.data_ptr(), _stream())
     _lib.check(rc, "amb_timestep_embedding")
     launch_count += 1
     return out

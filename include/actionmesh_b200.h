@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 3
+#define AMB_ABI_VERSION 4
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -55,11 +55,13 @@ int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, co
 /* ---- small elementwise helpers -------------------------------------------------------------------------------------
  * cast: fp32 -> bf16 (latents before proj_in, temporal_denoiser.py:205-206; context before to_k/to_v).
  * timestep embedding: diffusers Timesteps(num_channels=C, flip_sin_to_cos=False, downscale_freq_shift=0) as used at
- *   temporal_denoiser.py:57-61,213: out[r] = [sin(t_r*w_j) | cos(t_r*w_j)], w_j = exp(-ln(1e4) * j / (C/2)).
+ *   temporal_denoiser.py:57-61,209-213: t_r = t[r % n_t] * (1 - mask[r]) (mask may be NULL);
+ *   out[r] = [sin(t_r*w_j) | cos(t_r*w_j)], w_j = exp(-ln(1e4) * j / (C/2)).
  * add_bias_rows: y[r, :] += bias  (A.5: zero-context cross-attention collapses to to_out.0.bias, block.py:146).
  */
 int amb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, amb_stream_t stream);
-int amb_timestep_embedding(const float* t, int rows, int channels, void* out_bf16, amb_stream_t stream);
+int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows, int channels, void* out_bf16,
+                           amb_stream_t stream);
 int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream);
 
 /* ---- tcgen05 GEMM with fused epilogues: C = epi(A · Wᵀ) ----------------------------------------------------------------

@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE ONLY — regenerate tests/golden/*.pt from the reference's OWN modules (build container only).
+
+    python -m oracle.gen_golden
+
+Runs facebookresearch/actionmesh's unmodified `ActionMeshDenoiser`, `SchedulerFlow`, `ClassifierFreeGuidance`,
+`chunk_from`, `compute_rotary_embeddings`, `LatentBank` (imported from /root/reference on top of oracle/diffusers_shim.py)
+on seeded inputs and stores inputs + outputs.  Weights are NOT stored: they are re-derived from (config, seed) by
+oracle/synth.py, and loaded into the reference module with strict=True (which also pins the state-dict key names).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference_loader, synth  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+TINY = dict(num_layers=5, num_attention_heads=2, width=256, cross_attention_dim=128, in_channels=64, mlp_ratio=4.0)
+WIDE = dict(num_layers=3, num_attention_heads=16, width=2048, cross_attention_dim=1024, in_channels=64, mlp_ratio=4.0)
+
+
+def _model(ns, cfgd, seed):
+    m = ns.ActionMeshDenoiser(inflated_layers=tuple(range(cfgd["num_layers"])), **cfgd).eval()
+    sd = synth.make_state_dict(m, seed)
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def main():
+    ns = reference_loader.load()
+    os.makedirs(GOLD, exist_ok=True)
+    torch.set_grad_enabled(False)
+
+    # ---- known answers for host logic
+    host = {"schedule": {}, "chunk_from": {}}
+    for n in (4, 15, 30):
+        ts, ds = ns.SchedulerFlow(num_inference_steps=n, shift=3.0).get_schedule()
+        host["schedule"][n] = (ts, ds)
+    g = torch.Generator().manual_seed(44)
+    noise = ns.SchedulerFlow(num_inference_steps=4).get_noise([2048, 64], 1, 16, "cpu", g)
+    host["noise_seed44_head"] = noise[0, :2, :4, :8].clone()
+    host["noise_seed44_stats"] = (float(noise.mean()), float(noise.std()))
+    for args in ((0, 16, 16, 15), (0, 31, 16, 15), (0, 32, 16, 15), (0, 256, 16, 15), (5, 31, 16, 15), (30, 31, 16, 15),
+                 (7, 16, 16, 15), (20, 47, 16, 15), (0, 8, 16, 15)):
+        host["chunk_from"][args] = ns.chunk_from(*args)
+    cos, sin = ns.compute_rotary_embeddings(128, torch.arange(16.0))
+    host["rope_cos"], host["rope_sin"] = cos, sin
+    x = torch.randn(2, 3, 5, 128, generator=torch.Generator().manual_seed(1))
+    host["rope_apply_in"] = x
+    host["rope_apply_out"] = ns.apply_rotary_embedding(x, cos[:5], sin[:5])
+    cf = ns.ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
+    p = torch.randn(2, 3, 4, 8, generator=torch.Generator().manual_seed(2))
+    host["cfg_in"] = p.clone()
+    host["cfg_out"] = cf.aggregate_cfg(p.clone())
+    bank = ns.LatentBank(empty_dims=(4, 2))
+    bank.update(torch.tensor([3.0]), torch.ones(1, 4, 2))
+    lat, msk = bank.get(torch.tensor([2.0, 3.0, 4.0]), "cpu", add_batch_dim=True)
+    host["bank_get"] = (lat, msk)
+    torch.save(host, os.path.join(GOLD, "host_logic.pt"))
+
+    # ---- tiny denoiser: forward + 4-step CFG denoise through the reference scheduler
+    m = _model(ns, TINY, 1234)
+    lat, ctx, fs, mask = synth.make_inputs(1, 3, 31, 64, 9, 128, seed=5)
+    cfg_b = ns.ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
+    h_in, c_in, m_in, f_in = cfg_b.cfg_at_inference(lat, ctx, mask, fs)
+    t = torch.tensor([751.1210938, 751.1210938])
+    out, _ = m.forward(hidden_states=h_in, context=c_in, framestep=f_in, diffusion_time=t, mask=m_in)
+    sch = ns.SchedulerFlow(num_inference_steps=4, shift=3.0, is_additive=True)
+    den = sch.denoise(m, cfg_b, lat.clone(), ctx, device="cpu", mask=mask, framestep=fs)
+    # non-inflated variant (per-frame self-attention) and no-mask variant
+    m2 = ns.ActionMeshDenoiser(inflated_layers=(0, 2, 4), **TINY).eval()
+    m2.load_state_dict(synth.make_state_dict(m2, 1234), strict=True)
+    out2, _ = m2.forward(hidden_states=h_in, context=c_in, framestep=f_in, diffusion_time=t, mask=None)
+    torch.save({"config": TINY, "seed": 1234, "input_seed": 5, "forward_out": out, "denoise4_out": den,
+                "forward_out_partial_inflate_nomask": out2, "t": t},
+               os.path.join(GOLD, "denoiser_tiny.pt"))
+
+    # ---- full-width 3-layer model (covers the skip block at D=2048, 16 heads, F=8192, Dc=1024)
+    mw = _model(ns, WIDE, 77)
+    lat, ctx, fs, mask = synth.make_inputs(1, 2, 255, 64, 257, 1024, seed=6)
+    h_in, c_in, m_in, f_in = cfg_b.cfg_at_inference(lat, ctx, mask, fs)
+    t = torch.tensor([502.9850769, 502.9850769])
+    outw, _ = mw.forward(hidden_states=h_in, context=c_in, framestep=f_in, diffusion_time=t, mask=m_in)
+    torch.save({"config": WIDE, "seed": 77, "input_seed": 6, "forward_out": outw, "t": t},
+               os.path.join(GOLD, "denoiser_wide3.pt"))
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
+
+
+if __name__ == "__main__":
+    main()

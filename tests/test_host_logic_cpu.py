@@ -1,0 +1,59 @@
+"""Host-side mirror of the reference interfaces (no GPU): schedule, CFG, weight re-packing, windows."""
+import torch
+
+from conftest import load_golden
+from actionmesh_b200.denoiser import repack_cross_kv, repack_self_qkv
+from actionmesh_b200.guidance import ClassifierFreeGuidance
+from actionmesh_b200.scheduler import B200SchedulerFlow
+
+
+def test_schedule_matches_reference_known_answers():
+    host = load_golden("host_logic.pt")
+    for n, (ts, ds) in host["schedule"].items():
+        s = B200SchedulerFlow(num_inference_steps=n, shift=3.0)
+        a, b = s.get_schedule()
+        assert torch.equal(a, ts) and torch.equal(b, ds)
+
+
+def test_get_noise_stream_matches_reference():
+    host = load_golden("host_logic.pt")
+    g = torch.Generator().manual_seed(44)
+    n = B200SchedulerFlow(num_inference_steps=4).get_noise([2048, 64], 1, 16, "cpu", g)
+    assert n.shape == (1, 16, 2048, 64)
+    assert torch.equal(n[0, :2, :4, :8], host["noise_seed44_head"])
+
+
+def test_cfg_surface():
+    host = load_golden("host_logic.pt")
+    cf = ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
+    assert torch.allclose(cf.aggregate_cfg(host["cfg_in"].clone()), host["cfg_out"], atol=1e-5)
+    lat, ctx = torch.randn(1, 3, 4, 8), torch.randn(1, 3, 5, 6)
+    mask, fs = torch.tensor([[1.0, 0, 0]]), torch.tensor([[0.0, 1, 2]])
+    l2, c2, m2, f2 = cf.cfg_at_inference(lat, ctx, mask, fs)
+    assert l2.shape[0] == 2 and torch.equal(c2[0], torch.zeros_like(ctx[0])) and torch.equal(c2[1], ctx[0])
+    assert torch.equal(m2[0], m2[1]) and torch.equal(f2[0], f2[1])
+    assert torch.equal(cf.get_unobserved_mask(mask), mask == 0)
+    assert cf.branches() == [(0, 1), (1, 1)]
+    off = ClassifierFreeGuidance(inference_enabled=False)
+    assert off.branches() == [(1, 1)] and off.aggregate_cfg(lat) is lat
+
+
+def test_qkv_repack_equals_head_interleaved_split():
+    """permuting the rows of cat(Wq,Wk,Wv) once == the reference's split of cat(q,k,v) per head."""
+    torch.manual_seed(0)
+    H, dh, D = 4, 8, 32
+    wq, wk, wv = torch.randn(D, D), torch.randn(D, D), torch.randn(D, D)
+    x = torch.randn(5, D)
+    qkv = torch.cat([x @ wq.t(), x @ wk.t(), x @ wv.t()], -1).view(5, H, 3 * dh)
+    q_ref, k_ref, v_ref = qkv.split(dh, dim=-1)  # attention_processor.py:106-110
+    packed = x @ repack_self_qkv(wq, wk, wv, H).t()
+    q, k, v = packed[:, :D].view(5, H, dh), packed[:, D:2 * D].view(5, H, dh), packed[:, 2 * D:].view(5, H, dh)
+    assert torch.allclose(q, q_ref, atol=1e-5) and torch.allclose(k, k_ref, atol=1e-5) and torch.allclose(v, v_ref, atol=1e-5)
+    Dc = 16
+    wk2, wv2 = torch.randn(D, Dc), torch.randn(D, Dc)
+    c = torch.randn(7, Dc)
+    kv = torch.cat([c @ wk2.t(), c @ wv2.t()], -1).view(7, H, 2 * dh)
+    k_ref, v_ref = kv.split(dh, dim=-1)  # :111-115
+    packed = c @ repack_cross_kv(wk2, wv2, H).t()
+    assert torch.allclose(packed[:, :D].view(7, H, dh), k_ref, atol=1e-5)
+    assert torch.allclose(packed[:, D:].view(7, H, dh), v_ref, atol=1e-5)
