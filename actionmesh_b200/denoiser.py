@@ -362,7 +362,7 @@ class B200Denoiser:
             q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
             k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
             v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-            ops.flash_attn(q4, k4, v4, att.view(*view), scale)
+            ops.flash_attn(q4, k4, v4, att.view(*view), scale, tag="attn_self")
             ops.gemm(att, w[p + "s.o.w"], h, bias=w[p + "s.o.b"], residual=h_in)
             h_in = h
             # ---- cross-attention (block.py:146-149); zero-context batch elements reduce to + to_out.0.bias (A.5)
@@ -378,7 +378,7 @@ class B200Denoiser:
                 ops.gemm(xn[rows], w[p + "x.q"], qb, norm=dict(cols=D, seg=D, w0=w[p + "x.nq"], eps=1e-6))
                 kvb = st.ctx_kv[i][b * T * S:(b + 1) * T * S]
                 ops.flash_attn(qb.view(T, L, H, dh), kvb[:, 0:D].view(T, S, H, dh), kvb[:, D:2 * D].view(T, S, H, dh),
-                               att[rows].view(T, L, H, dh), scale)
+                               att[rows].view(T, L, H, dh), scale, tag="attn_cross")
                 ops.gemm(att[rows], w[p + "x.o.w"], h[rows], bias=w[p + "x.o.b"], residual=h[rows])
             # ---- feed-forward (block.py:152)
             ops.layernorm(h, w[p + "norm_ff.g"], w[p + "norm_ff.b"], 1e-5, out=xn)

@@ -14,6 +14,28 @@ from . import _lib
 
 launch_count = 0
 
+# Optional per-kernel CUDA-event timing (bench.py's roofline leg): when `event_log` is a list, flash_attn / gemm calls
+# whose `tag` is in `event_tags` append (tag, start_event, end_event) recorded on the launching stream.
+event_log = None
+event_tags: set = set()
+
+
+class _Timed:
+    def __init__(self, tag):
+        self.on = event_log is not None and tag in event_tags
+        self.tag = tag
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e1.record()
+            event_log.append((self.tag, self.e0, self.e1))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -113,7 +135,7 @@ def add_bias_rows(y: torch.Tensor, bias: torch.Tensor) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          a2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
          col_scale: Optional[torch.Tensor] = None, row_map: Optional[tuple[int, int, int]] = None,
-         norm: Optional[dict] = None) -> torch.Tensor:
+         norm: Optional[dict] = None, tag: str = "gemm") -> torch.Tensor:
     """out = epilogue(cat[a, a2] @ w.T).  a:(m,k1) bf16, a2:(m,k2) bf16 or None, w:(n,k1+k2) bf16, out bf16/fp32.
 
     norm = dict(cols=, seg=, w0=, w1=, eps=, rope_cols=, cos=, sin=, rows_per_pos=) enables the per-head
@@ -169,14 +191,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         g.norm_w0 = g.norm_w1 = g.rope_cos = g.rope_sin = None
         g.norm_eps = 0.0
         g.rope_rows_per_pos = 1
-    rc = _lib.load_library().amb_gemm_bf16(C.byref(g), _stream())
+    with _Timed(tag):
+        rc = _lib.load_library().amb_gemm_bf16(C.byref(g), _stream())
     _lib.check(rc, "amb_gemm_bf16")
     launch_count += 1
     return out
 
 
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float, *,
-               kv_chunks: int = 1) -> torch.Tensor:
+               kv_chunks: int = 1, tag: str = "attn") -> torch.Tensor:
     """softmax(scale q kᵀ) v, non-causal.  q:(B,Sq,H,D) k,v:(B,Sk,H,D) out:(B,Sq,H,D) — arbitrary (16-byte aligned)
     strides with unit stride on D, so views into a fused QKV buffer work in place.
 
@@ -206,7 +229,8 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
     a.kv_chunks = kv_chunks
     a.batch, a.heads, a.sq, a.head_dim = B, H, Sq, D
     a.scale = float(scale)
-    rc = _lib.load_library().amb_flash_attn_fwd(C.byref(a), _stream())
+    with _Timed(tag):
+        rc = _lib.load_library().amb_flash_attn_fwd(C.byref(a), _stream())
     _lib.check(rc, "amb_flash_attn_fwd")
     launch_count += 1
     return out
