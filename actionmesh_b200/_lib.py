@@ -10,11 +10,11 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libactionmesh_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 EXPORTS = [
     "amb_last_error", "amb_abi_version", "amb_device_info", "amb_cfg_euler_step", "amb_layernorm",
-    "amb_cast_f32_bf16", "amb_timestep_embedding", "amb_add_bias_rows", "amb_gemm_bf16", "amb_flash_attn_fwd",
+    "amb_cast_f32_bf16", "amb_patchify", "amb_timestep_embedding", "amb_add_bias_rows", "amb_gemm_bf16", "amb_flash_attn_fwd",
 ]
 
 
@@ -79,9 +79,10 @@ def load_library() -> C.CDLL:
         C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
     ]
     lib.amb_layernorm.argtypes = [
-        C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int,
+        C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int,
         C.c_float, C.c_void_p,
     ]
+    lib.amb_patchify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.amb_cast_f32_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.amb_timestep_embedding.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.amb_add_bias_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]

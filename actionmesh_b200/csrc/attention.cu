@@ -10,6 +10,7 @@
 //               when the running max grew by more than 2^8), which is exact after the final 1/rowsum normalisation.
 // TMEM: S0 [0,64) S1 [64,128) O0 [128,128+D) O1 [128+D,128+2D)  -> 512 columns allocated.
 // The issue order  S0 S1 | PV0 S0' PV1 S1' | ...  keeps the tensor pipe busy with tile 1 while warpgroup 0 is in softmax.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/actionmesh_b200.h"
@@ -299,9 +300,321 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
 }
 
-template <int D, int STAGES>
+
+// =====================================================================================================================
+// v2 (head_dim 128): 128-key K/V tiles, P kept in TMEM (aliasing S, consumed by a TS-form MMA), P handed over in two
+// halves so the P·V MMAs of the first 64 keys overlap the exponentials of the last 64.
+//   warps 0-3  softmax warpgroup, query tile 0      warps 4-7  softmax warpgroup, query tile 1
+//   warp 8     TMA producer (Q once; K ring, V ring) warp 9     MMA issuer + TMEM owner
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i = bf16 pairs in columns [0,64) of S_i.
+// Tensor-pipe order:  S0 S1 | PV0a PV0b S0' | PV1a PV1b S1' | ...
+// =====================================================================================================================
+constexpr int V2_BK = 128;
+constexpr int V2_THREADS = 320;
+
+template <int KSTAGES, int VSTAGES>
+struct AttnV2Smem {
+  static constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column halves of [128 rows x 128 B]
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = 2 * TILE_BYTES;
+  static constexpr int V_OFF = K_OFF + KSTAGES * TILE_BYTES;
+  static constexpr int BAR_OFF = V_OFF + VSTAGES * TILE_BYTES;
+  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 2 + 2 + 2 + 2;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int KSTAGES, int VSTAGES>
+__global__ void __launch_bounds__(V2_THREADS, 1)
+flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnV2Smem<KSTAGES, VSTAGES>;
+  constexpr int D = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + KSTAGES;
+  uint64_t* v_full = k_empty + KSTAGES;
+  uint64_t* v_empty = v_full + VSTAGES;
+  uint64_t* s_full = v_empty + VSTAGES;  // [2]
+  uint64_t* p_a = s_full + 2;            // [2] first 64 keys of P ready
+  uint64_t* p_b = p_a + 2;               // [2] last 64 keys of P ready
+  uint64_t* o_full = p_b + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int tiles_per_chunk = (p.sk_chunk + V2_BK - 1) / V2_BK;
+  const int n_kv = p.kv_chunks * tiles_per_chunk;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_a[i], 128);
+        mbar_init(&p_b[i], 128);
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      mbar_expect_tx(q_full, 2 * L::TILE_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d(smem + L::Q_OFF + i * L::TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
+                      batch, kEvictFirst);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        const int chunk = j / tiles_per_chunk;
+        const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
+        const int c3 = batch * p.kv_chunks + chunk;
+        mbar_wait(&k_empty[ks], kph ^ 1);
+        mbar_expect_tx(&k_full[ks], L::TILE_BYTES);
+        uint8_t* sk = smem + L::K_OFF + ks * L::TILE_BYTES;
+        tma_load_4d(sk, &tmK, &k_full[ks], 0, key0, head, c3, kEvictLast);
+        tma_load_4d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, c3, kEvictLast);
+        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+        mbar_wait(&v_empty[vs], vph ^ 1);
+        mbar_expect_tx(&v_full[vs], L::TILE_BYTES);
+        uint8_t* sv = smem + L::V_OFF + vs * L::TILE_BYTES;
+        tma_load_4d(sv, &tmV, &v_full[vs], 0, key0, head, c3, kEvictLast);
+        tma_load_4d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, c3, kEvictLast);
+        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V2_BK, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
+      const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+      const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
+      const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
+
+      auto issue_qk = [&](int i, int kstage) {
+        const uint32_t qa = sq_addr + i * L::TILE_BYTES;
+        const uint32_t ka = sk_addr + kstage * L::TILE_BYTES;
+        const uint32_t d = tmem_base + i * 128;
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
+          mma_ss(d, make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(ka + off), idesc_qk, k != 0);
+        }
+        tc_commit(&s_full[i]);
+      };
+      auto issue_pv_half = [&](int i, int vstage, int half, bool first_tile) {
+        const uint32_t va = sv_addr + vstage * L::TILE_BYTES;
+        const uint32_t d = tmem_base + 256 + i * 128;
+        const uint32_t pa = tmem_base + i * 128;  // P aliases S_i: 16 keys = 8 columns
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = half * 4 + kk;
+          mma_ts(d, pa + k * 8, make_desc_mnmajor_sw128(va + k * 2048, 16384), idesc_pv,
+                 (!first_tile || k != 0) ? 1u : 0u);
+        }
+      };
+
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      tc_commit(&k_empty[0]);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int j = 0; j < n_kv; ++j) {
+        int ks_next = ks + 1;
+        uint32_t kph_next = kph;
+        if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
+        const bool has_next = (j + 1 < n_kv);
+        const uint32_t par = j & 1;
+        mbar_wait(&v_full[vs], vph);
+        // ---- tile 0
+        mbar_wait(&p_a[0], par);
+        tc_fence_after();
+        issue_pv_half(0, vs, 0, j == 0);
+        mbar_wait(&p_b[0], par);
+        tc_fence_after();
+        issue_pv_half(0, vs, 1, j == 0);
+        if (has_next) {
+          mbar_wait(&k_full[ks_next], kph_next);
+          tc_fence_after();
+          issue_qk(0, ks_next);
+        } else {
+          tc_commit(&o_full[0]);
+        }
+        // ---- tile 1
+        mbar_wait(&p_a[1], par);
+        tc_fence_after();
+        issue_pv_half(1, vs, 0, j == 0);
+        mbar_wait(&p_b[1], par);
+        tc_fence_after();
+        issue_pv_half(1, vs, 1, j == 0);
+        tc_commit(&v_empty[vs]);
+        if (has_next) {
+          issue_qk(1, ks_next);
+          tc_commit(&k_empty[ks_next]);
+        } else {
+          tc_commit(&o_full[1]);
+        }
+        ks = ks_next;
+        kph = kph_next;
+        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int wg = warp >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + wg * ATT_BQ + row_in_tile;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_base + wg * 128 + lane_sel;
+    const uint32_t o_addr = tmem_base + 256 + wg * 128 + lane_sel;
+
+    float m_used = -INFINITY;
+    float row_sum = 0.f;
+    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V2_BK;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[wg], j & 1);
+      tc_fence_after();
+      const int jj = j % tiles_per_chunk;
+      const int valid = (jj == tiles_per_chunk - 1) ? last_valid : V2_BK;
+      // ---- pass 1: row max over the 128 scores
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < V2_BK; c += 64) {
+        float a[32], b[32];
+        tmem_ld_x32f(s_addr + c, a);
+        tmem_ld_x32f(s_addr + c + 32, b);
+        tmem_wait_ld();
+        if (valid < V2_BK) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            if (c + t >= valid) a[t] = -INFINITY;
+            if (c + 32 + t >= valid) b[t] = -INFINITY;
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          mx = fmaxf(mx, fmaxf(a[t], a[t + 1]));
+          mx = fmaxf(mx, fmaxf(b[t], b[t + 1]));
+        }
+      }
+      const float m_new = fmaxf(m_used, mx);
+      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
+        if (need) {
+          m_used = m_new;
+          row_sum *= alpha;
+        }
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float ov[32];
+          tmem_ld_x32f(o_addr + c, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
+          tmem_st_x32f(o_addr + c, ov);
+        }
+        tmem_wait_st();
+      }
+      // ---- pass 2: exponentials, bf16 P written over the consumed S columns
+      const float mb = m_used * p.scale_log2;
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float sv[32];
+        tmem_ld_x32f(s_addr + c * 32, sv);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float e0 = ex2_approx(fmaf(sv[t], p.scale_log2, -mb));
+          float e1 = ex2_approx(fmaf(sv[t + 1], p.scale_log2, -mb));
+          if (valid < V2_BK) {
+            if (c * 32 + t >= valid) e0 = 0.f;
+            if (c * 32 + t + 1 >= valid) e1 = 0.f;
+          }
+          psum += e0 + e1;
+          pk[t >> 1] = pack_bf16(e0, e1);
+        }
+        tmem_st_x16(s_addr + c * 16, pk);
+        if (c == 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_a[wg]);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_b[wg]);
+      row_sum += psum;
+    }
+
+    mbar_wait(&o_full[wg], 0);
+    tc_fence_after();
+    const float inv = 1.0f / row_sum;
+    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + (long long)q_row * p.o_stride_s;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      float ov[32];
+      tmem_ld_x32f(o_addr + c, ov);
+      tmem_wait_ld();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
+          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
+          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
+          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c + t) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, int STAGES, bool V2>
 static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   using L = AttnSmem<D, STAGES>;
+  using L2 = AttnV2Smem<2, 2>;
+  constexpr int BKV = V2 ? V2_BK : ATT_BK;
   CUtensorMap tmQ, tmK, tmV;
   const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
   const int sk_chunk = chunks > 1 ? a->sk_chunk : a->sk;
@@ -326,7 +639,7 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
     }
     uint64_t dims[4] = {(uint64_t)D, (uint64_t)sk_chunk, (uint64_t)a->heads, (uint64_t)a->batch * chunks};
     uint64_t str[3] = {(uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)outer_stride * 2};
-    uint32_t box[4] = {64, ATT_BK, 1, 1};
+    uint32_t box[4] = {64, BKV, 1, 1};
     return encode_tmap_bf16(tm, base, 4, dims, str, box);
   };
   int r = enc_kv(&tmK, a->k, a->k_stride_s, a->k_stride_h, a->k_stride_b, a->k_chunk_stride);
@@ -341,14 +654,23 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   p.kv_chunks = chunks; p.sk_chunk = sk_chunk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
 
-  auto kern = flash_attn_fwd_kernel<D, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
-  }
   dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
-  kern<<<grid, ATT_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  static bool attr_set = false;
+  if constexpr (V2) {
+    auto kern = flash_attn_fwd_v2_kernel<2, 2>;
+    if (!attr_set) {
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      attr_set = true;
+    }
+    kern<<<grid, V2_THREADS, L2::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    auto kern = flash_attn_fwd_kernel<D, STAGES>;
+    if (!attr_set) {
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+      attr_set = true;
+    }
+    kern<<<grid, ATT_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  }
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }
@@ -370,6 +692,7 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
                 "flash_attn: kv_chunks * sk_chunk must equal sk");
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
-  if (a->head_dim == 128) return launch_attn<128, 3>(a, s);
-  return launch_attn<64, 4>(a, s);
+  static const int force_v1 = []() { const char* e = getenv("AMB_ATTN_V1"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (a->head_dim == 128) return force_v1 ? launch_attn<128, 3, false>(a, s) : launch_attn<128, 3, true>(a, s);
+  return launch_attn<64, 4, false>(a, s);
 }

@@ -63,10 +63,10 @@ __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) 
 // One warp per row; the row (<= 4096 elements) is held in registers between the statistics and the normalise pass, so
 // HBM sees exactly one read and one write of the row.  Two-pass (mean, then centred variance) in fp32 like
 // F.layer_norm on an fp32 upcast.
-template <int COLS, bool XF32>
+template <int COLS, bool XF32, bool YF32>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, long long ldx,
                                                         const float* __restrict__ gamma,
-                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                                        const float* __restrict__ beta, void* __restrict__ yv,
                                                         long long ldy, long long rows, float eps) {
   constexpr int PER_LANE = COLS / 32;   // elements per lane
   constexpr int VEC = PER_LANE / 8;     // 8-element vectors per lane
@@ -108,12 +108,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q * (1.0f / COLS) + eps);
-  __nv_bfloat16* yr = y + row * ldy;
 #pragma unroll
   for (int j = 0; j < VEC; ++j) {
     const int c = (j * 32 + lane) * 8;
     const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    if constexpr (YF32) {
+      float* yr = reinterpret_cast<float*>(yv) + row * ldy + c;
+      reinterpret_cast<float4*>(yr)[0] = make_float4((v[j * 8 + 0] - mean) * rstd * g0.x + b0.x, (v[j * 8 + 1] - mean) * rstd * g0.y + b0.y,
+                                                     (v[j * 8 + 2] - mean) * rstd * g0.z + b0.z, (v[j * 8 + 3] - mean) * rstd * g0.w + b0.w);
+      reinterpret_cast<float4*>(yr)[1] = make_float4((v[j * 8 + 4] - mean) * rstd * g1.x + b1.x, (v[j * 8 + 5] - mean) * rstd * g1.y + b1.y,
+                                                     (v[j * 8 + 6] - mean) * rstd * g1.z + b1.z, (v[j * 8 + 7] - mean) * rstd * g1.w + b1.w);
+      continue;
+    }
+    __nv_bfloat16* yr = reinterpret_cast<__nv_bfloat16*>(yv) + row * ldy;
     uint4 o;
     o.x = pack_bf16((v[j * 8 + 0] - mean) * rstd * g0.x + b0.x, (v[j * 8 + 1] - mean) * rstd * g0.y + b0.y);
     o.y = pack_bf16((v[j * 8 + 2] - mean) * rstd * g0.z + b0.z, (v[j * 8 + 3] - mean) * rstd * g0.w + b0.w);
@@ -175,6 +183,26 @@ __global__ void __launch_bounds__(256) add_bias_rows_kernel(__nv_bfloat16* __res
   }
 }
 
+// DinoV2 patch embedding as a GEMM: im2col of (T,3,H,W) fp32 pixels into bf16 rows (t, py, px) x cols (c, ky, kx),
+// zero-padded from 3*P*P to `kpad` columns (HF Dinov2PatchEmbeddings is Conv2d(3, D, P, stride P)).
+__global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out,
+                                                       int T, int H, int W, int P, int kpad) {
+  const int gw = W / P, gh = H / P;
+  const long long total = (long long)T * gh * gw * kpad;
+  const int kreal = 3 * P * P;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % kpad);
+    const long long row = i / kpad;
+    float v = 0.f;
+    if (col < kreal) {
+      const int c = col / (P * P), r = col % (P * P), ky = r / P, kx = r % P;
+      const int px = (int)(row % gw), py = (int)((row / gw) % gh), t = (int)(row / ((long long)gw * gh));
+      v = pix[(((long long)t * 3 + c) * H + (py * P + ky)) * W + (px * P + kx)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 static int grid_for(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;  // grid-stride loops; a few waves of resident CTAs
@@ -218,19 +246,20 @@ int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, co
   return AMB_OK;
 }
 
-int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y, int y_fp32,
                   int64_t ldy, int64_t rows, int cols, float eps, amb_stream_t stream) {
-  AMB_CHECK_ARG(x && gamma && beta && y_bf16, "layernorm: null pointer");
+  AMB_CHECK_ARG(x && gamma && beta && y, "layernorm: null pointer");
   AMB_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "layernorm: row strides must be multiples of 8 elements");
   if (rows <= 0) return AMB_OK;
   const int wpb = 8;
   dim3 grid((unsigned)((rows + wpb - 1) / wpb)), block(wpb * 32);
   cudaStream_t s = (cudaStream_t)stream;
-  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(y_bf16);
-#define AMB_LN_CASE(C)                                                                                           \
-  case C:                                                                                                        \
-    if (x_fp32) layernorm_kernel<C, true><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);         \
-    else layernorm_kernel<C, false><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);               \
+#define AMB_LN_CASE(C)                                                                                                   \
+  case C:                                                                                                                \
+    if (x_fp32 && y_fp32) layernorm_kernel<C, true, true><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);  \
+    else if (x_fp32) layernorm_kernel<C, true, false><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);      \
+    else if (y_fp32) layernorm_kernel<C, false, true><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);      \
+    else layernorm_kernel<C, false, false><<<grid, block, 0, s>>>(x, ldx, gamma, beta, y, ldy, rows, eps);                 \
     break;
   switch (cols) {
     AMB_LN_CASE(256)
@@ -243,6 +272,19 @@ int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, co
       return AMB_ERR_UNSUPPORTED;
   }
 #undef AMB_LN_CASE
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_patchify(const float* pixels, void* out_bf16, int n_images, int height, int width, int patch, int kpad,
+                 amb_stream_t stream) {
+  AMB_CHECK_ARG(pixels && out_bf16, "patchify: null pointer");
+  AMB_CHECK_ARG(patch > 0 && height % patch == 0 && width % patch == 0 && kpad >= 3 * patch * patch && kpad % 64 == 0,
+                "patchify: bad geometry h=%d w=%d p=%d kpad=%d", height, width, patch, kpad);
+  if (n_images <= 0) return AMB_OK;
+  const long long total = (long long)n_images * (height / patch) * (width / patch) * kpad;
+  patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(pixels, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+                                                                           n_images, height, width, patch, kpad);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -1,0 +1,173 @@
+"""B200ImageEncoder — DinoV2-L/14 frame encoder behind the reference's ImageEncoder surface.
+
+Mirrors actionmesh/model/image_encoder.py:16-55: constructor kwargs `pretrained_dino_feature_extractor`,
+`pretrained_dino_model`; `.encode_images(list[PIL]) -> (T, 257, 1024) fp32`; `.device`, `.eval()`, `.to()`.
+The transformer (HF `Dinov2Model`, transformers/models/dinov2/modeling_dinov2.py: patch-embed conv, CLS + interpolated
+position embeddings, 24 x [LN, MHA(16 heads, d_h 64), LayerScale, LN, MLP GELU, LayerScale], final LN) runs on the sm_100a
+kernels: patchify (im2col) -> tcgen05 GEMM, LayerNorm, fused-QKV tcgen05 GEMM, tcgen05 flash attention (head_dim 64),
+GEMM epilogues with bias / GELU / LayerScale / fp32 residual.  The residual stream is kept in fp32 (the reference runs
+DinoV2 in fp32, outside autocast, pipeline.py:664-667); GEMM operands are bf16 with fp32 accumulation.
+
+Image preprocessing stays on the host exactly like the reference (HF BitImageProcessor: bicubic resize to 256, centre
+crop 224, 1/255 rescale, ImageNet mean/std); it is listed as "next" in SURVEY 8(f).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from ._lib import AmbError
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def default_preprocessor():
+    """facebook/dinov2-large preprocessor_config (hub file, not available offline): shortest_edge 256 bicubic, centre
+    crop 224, rescale 1/255, ImageNet normalisation."""
+    from transformers import BitImageProcessor
+
+    return BitImageProcessor(do_resize=True, size={"shortest_edge": 256}, resample=3, do_center_crop=True,
+                             crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255.0,
+                             do_normalize=True, image_mean=list(IMAGENET_MEAN), image_std=list(IMAGENET_STD),
+                             do_convert_rgb=True)
+
+
+class B200ImageEncoder:
+    def __init__(self, pretrained_dino_feature_extractor: Optional[str] = None,
+                 pretrained_dino_model: Optional[str] = None, *, hidden_size: int = 1024, num_layers: int = 24,
+                 num_heads: int = 16, patch_size: int = 14, image_size: int = 224, mlp_ratio: int = 4,
+                 layer_norm_eps: float = 1e-6):
+        self.hidden_size, self.num_layers, self.num_heads = hidden_size, num_layers, num_heads
+        self.patch_size, self.image_size, self.mlp_ratio, self.eps = patch_size, image_size, mlp_ratio, layer_norm_eps
+        if hidden_size // num_heads != 64 or hidden_size % 256:
+            raise AmbError("B200ImageEncoder: head_dim must be 64 and hidden_size a multiple of 256")
+        self._device = torch.device("cpu")
+        self._w: dict = {}
+        self._loaded = False
+        self._pending_sd = None
+        self.image_preprocess_dino = None
+        if pretrained_dino_feature_extractor is not None and os.path.isdir(pretrained_dino_feature_extractor):
+            from transformers import BitImageProcessor
+            self.image_preprocess_dino = BitImageProcessor.from_pretrained(pretrained_dino_feature_extractor)
+        if self.image_preprocess_dino is None:
+            self.image_preprocess_dino = default_preprocessor()
+        if pretrained_dino_model is not None and os.path.isdir(pretrained_dino_model):
+            from safetensors.torch import load_file
+            st = os.path.join(pretrained_dino_model, "model.safetensors")
+            self._pending_sd = load_file(st) if os.path.exists(st) else torch.load(
+                os.path.join(pretrained_dino_model, "pytorch_model.bin"), map_location="cpu")
+
+    # ---- module-like surface
+    @property
+    def device(self) -> torch.device:
+        return self._device
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise AmbError("B200ImageEncoder runs on CUDA (sm_100a) only")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self._device = device
+        if self._pending_sd is not None:
+            self.load_state_dict(self._pending_sd)
+            self._pending_sd = None
+        elif self._loaded:
+            self._w = {k: v.to(device) for k, v in self._w.items()}
+        return self
+
+    # ---- weights (HF Dinov2Model state-dict keys)
+    def load_state_dict(self, sd: dict) -> None:
+        dev = self._device
+        if dev.type != "cuda":
+            raise AmbError("call .to('cuda') before load_state_dict")
+        sd = {k[len("dinov2."):] if k.startswith("dinov2.") else k: v for k, v in sd.items()}
+        D, P = self.hidden_size, self.patch_size
+        f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
+        W = lambda t: t.to(torch.bfloat16).contiguous()
+        w = {}
+        kreal = 3 * P * P
+        self.kpad = (kreal + 63) // 64 * 64
+        pw = torch.zeros(D, self.kpad, device=dev)
+        pw[:, :kreal] = f32("embeddings.patch_embeddings.projection.weight").reshape(D, kreal)
+        w["patch.w"], w["patch.b"] = W(pw), f32("embeddings.patch_embeddings.projection.bias").contiguous()
+        # position embeddings interpolated once for the fixed 224x224 grid (modeling_dinov2 interpolate_pos_encoding:
+        # bicubic, align_corners=False, fp32), CLS position kept; + cls token folded into row 0.
+        pos = f32("embeddings.position_embeddings")[0]
+        n_side_src = int(math.isqrt(pos.shape[0] - 1))
+        g = self.image_size // P
+        grid = pos[1:].reshape(1, n_side_src, n_side_src, D).permute(0, 3, 1, 2)
+        if n_side_src != g:
+            grid = torch.nn.functional.interpolate(grid, size=(g, g), mode="bicubic", align_corners=False)
+        grid = grid.permute(0, 2, 3, 1).reshape(g * g, D)
+        base = torch.cat([(f32("embeddings.cls_token")[0, 0] + pos[0])[None], grid], dim=0)  # (1+g*g, D)
+        w["base"] = base.contiguous()
+        for i in range(self.num_layers):
+            p = f"encoder.layer.{i}."
+            w[p + "n1.g"], w[p + "n1.b"] = f32(p + "norm1.weight").contiguous(), f32(p + "norm1.bias").contiguous()
+            a = p + "attention.attention."
+            w[p + "qkv.w"] = W(torch.cat([f32(a + "query.weight"), f32(a + "key.weight"), f32(a + "value.weight")], 0))
+            w[p + "qkv.b"] = torch.cat([f32(a + "query.bias"), f32(a + "key.bias"), f32(a + "value.bias")], 0).contiguous()
+            w[p + "o.w"], w[p + "o.b"] = W(f32(p + "attention.output.dense.weight")), f32(p + "attention.output.dense.bias").contiguous()
+            w[p + "ls1"] = f32(p + "layer_scale1.lambda1").contiguous()
+            w[p + "n2.g"], w[p + "n2.b"] = f32(p + "norm2.weight").contiguous(), f32(p + "norm2.bias").contiguous()
+            w[p + "fc1.w"], w[p + "fc1.b"] = W(f32(p + "mlp.fc1.weight")), f32(p + "mlp.fc1.bias").contiguous()
+            w[p + "fc2.w"], w[p + "fc2.b"] = W(f32(p + "mlp.fc2.weight")), f32(p + "mlp.fc2.bias").contiguous()
+            w[p + "ls2"] = f32(p + "layer_scale2.lambda1").contiguous()
+        w["ln.g"], w["ln.b"] = f32("layernorm.weight").contiguous(), f32("layernorm.bias").contiguous()
+        self._w = w
+        self._loaded = True
+
+    # ---- encode
+    @torch.no_grad()
+    def encode_images(self, images: List) -> torch.Tensor:
+        """images: list of T PIL images -> context (T, 257, 1024) fp32 (image_encoder.py:38-55)."""
+        pixel_values = self.image_preprocess_dino.preprocess(images, return_tensors="pt").pixel_values
+        return self.encode_pixel_values(pixel_values)
+
+    @torch.no_grad()
+    def encode_pixel_values(self, pixel_values: torch.Tensor) -> torch.Tensor:
+        """pixel_values (T,3,224,224) fp32 (host or device) -> last_hidden_state (T, 1+g*g, D) fp32."""
+        if not self._loaded:
+            raise AmbError("B200ImageEncoder: weights not loaded")
+        w = self._w
+        dev = self._device
+        px = pixel_values.to(device=dev, dtype=torch.float32).contiguous()
+        T = px.shape[0]
+        D, H, P = self.hidden_size, self.num_heads, self.patch_size
+        g = self.image_size // P
+        L = 1 + g * g
+        M = T * L
+        F_ = D * self.mlp_ratio
+        bf = torch.bfloat16
+        x = w["base"].repeat(T, 1)                      # (M, D) fp32 residual stream: cls+pos rows (device copy)
+        patches = ops.patchify(px, P, self.kpad)
+        ops.gemm(patches, w["patch.w"], x, bias=w["patch.b"], residual=x, row_map=(g * g, L, 1))
+        xn = torch.empty(M, D, dtype=bf, device=dev)
+        qkv = torch.empty(M, 3 * D, dtype=bf, device=dev)
+        att = torch.empty(M, D, dtype=bf, device=dev)
+        hid = torch.empty(M, F_, dtype=bf, device=dev)
+        scale = 1.0 / math.sqrt(D // H)
+        for i in range(self.num_layers):
+            p = f"encoder.layer.{i}."
+            ops.layernorm(x, w[p + "n1.g"], w[p + "n1.b"], self.eps, out=xn)
+            ops.gemm(xn, w[p + "qkv.w"], qkv, bias=w[p + "qkv.b"])
+            q4 = qkv[:, 0:D].unflatten(0, (T, L)).unflatten(-1, (H, D // H))
+            k4 = qkv[:, D:2 * D].unflatten(0, (T, L)).unflatten(-1, (H, D // H))
+            v4 = qkv[:, 2 * D:].unflatten(0, (T, L)).unflatten(-1, (H, D // H))
+            ops.flash_attn(q4, k4, v4, att.view(T, L, H, D // H), scale, tag="attn_dino")
+            ops.gemm(att, w[p + "o.w"], x, bias=w[p + "o.b"], col_scale=w[p + "ls1"], residual=x)
+            ops.layernorm(x, w[p + "n2.g"], w[p + "n2.b"], self.eps, out=xn)
+            ops.gemm(xn, w[p + "fc1.w"], hid, bias=w[p + "fc1.b"], act=1)
+            ops.gemm(hid, w[p + "fc2.w"], x, bias=w[p + "fc2.b"], col_scale=w[p + "ls2"], residual=x)
+        out = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.layernorm(x, w["ln.g"], w["ln.b"], self.eps, out=out)
+        return out.view(T, L, D)

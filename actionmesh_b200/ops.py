@@ -73,7 +73,7 @@ def cfg_euler_step(latents: torch.Tensor, pred: torch.Tensor, scales: list[float
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Affine LayerNorm over the last dim of a 2-D (rows, cols) tensor, fp32 statistics, bf16 output."""
+    """Affine LayerNorm over the last dim of a 2-D (rows, cols) tensor, fp32 statistics, bf16 (default) or fp32 output."""
     global launch_count
     assert x.dim() == 2 and x.stride(1) == 1
     rows, cols = x.shape
@@ -81,13 +81,29 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
     _need(gamma, torch.float32, "gamma")
     _need(beta, torch.float32, "beta")
-    _need(out, torch.bfloat16, "out")
-    if x.dtype not in (torch.bfloat16, torch.float32):
-        raise _lib.AmbError(f"layernorm: unsupported dtype {x.dtype}")
+    if x.dtype not in (torch.bfloat16, torch.float32) or out.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.AmbError(f"layernorm: unsupported dtype {x.dtype} -> {out.dtype}")
+    if not out.is_cuda:
+        raise _lib.AmbError("layernorm: out must be a CUDA tensor")
     rc = _lib.load_library().amb_layernorm(
         x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-        out.stride(0), rows, cols, float(eps), _stream())
+        int(out.dtype == torch.float32), out.stride(0), rows, cols, float(eps), _stream())
     _lib.check(rc, "amb_layernorm")
+    launch_count += 1
+    return out
+
+
+def patchify(pixels: torch.Tensor, patch: int, kpad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """im2col of (T,3,H,W) fp32 pixels -> (T*(H/P)*(W/P), kpad) bf16 rows for the patch-embedding GEMM."""
+    global launch_count
+    _need(pixels, torch.float32, "pixels")
+    assert pixels.is_contiguous() and pixels.dim() == 4 and pixels.shape[1] == 3
+    T, _, H, W = pixels.shape
+    rows = T * (H // patch) * (W // patch)
+    if out is None:
+        out = torch.empty(rows, kpad, dtype=torch.bfloat16, device=pixels.device)
+    rc = _lib.load_library().amb_patchify(pixels.data_ptr(), out.data_ptr(), T, H, W, patch, kpad, _stream())
+    _lib.check(rc, "amb_patchify")
     launch_count += 1
     return out
 

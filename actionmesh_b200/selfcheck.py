@@ -36,6 +36,6 @@ def smoke_check(verbose: bool = True) -> float:
     err = float((out - ref).norm() / ref.norm())
     if verbose:
         print(f"smoke: 1 denoiser step (CFG x2, 3 blocks) on cuda:0 vs fp32 oracle: rel err {err:.3e}")
-    if not (err < 2e-2) or not torch.equal(out[0, 0], lat[0, 0]):
+    if not (err < 4e-2) or not torch.equal(out[0, 0], lat[0, 0]):
         raise RuntimeError(f"smoke parity failed: rel err {err}")
     return err

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 4
+#define AMB_ABI_VERSION 5
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -47,9 +47,9 @@ int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, co
 /* ---- LayerNorm (affine, fp32 statistics) ---------------------------------------------------------------------------
  * Replaces diffusers FP32LayerNorm at actionmesh/model/utils/block.py:64,83,98,107 and nn.LayerNorm at
  * actionmesh/model/temporal_denoiser.py:108,239; also DinoV2's LayerNorms (transformers modeling_dinov2).
- * x: (rows, cols) bf16 or fp32 (x_fp32), y: bf16.  cols must be a multiple of 256 and <= 4096.
+ * x: (rows, cols) bf16 or fp32 (x_fp32), y: bf16 or fp32 (y_fp32).  cols in {256, 512, 1024, 2048, 4096}.
  */
-int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y_bf16,
+int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, const float* beta, void* y, int y_fp32,
                   int64_t ldy, int64_t rows, int cols, float eps, amb_stream_t stream);
 
 /* ---- small elementwise helpers -------------------------------------------------------------------------------------
@@ -60,6 +60,11 @@ int amb_layernorm(const void* x, int x_fp32, int64_t ldx, const float* gamma, co
  * add_bias_rows: y[r, :] += bias  (A.5: zero-context cross-attention collapses to to_out.0.bias, block.py:146).
  */
 int amb_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, amb_stream_t stream);
+/* patchify: im2col for DinoV2's Conv2d(3, D, P, stride P) patch embedding (HF modeling_dinov2 Dinov2PatchEmbeddings, called
+ * from actionmesh/model/image_encoder.py:53): pixels (T,3,H,W) fp32 -> bf16 rows (t,py,px) x cols (c,ky,kx), zero padded to
+ * kpad (multiple of 64) columns so the projection runs on amb_gemm_bf16. */
+int amb_patchify(const float* pixels, void* out_bf16, int n_images, int height, int width, int patch, int kpad,
+                 amb_stream_t stream);
 int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows, int channels, void* out_bf16,
                            amb_stream_t stream);
 int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream);

@@ -80,7 +80,7 @@ def test_argument_validation_fails_loudly(amb_lib):
     a.head_dim = 96
     rc = amb_lib.amb_flash_attn_fwd(C.byref(a), None)
     assert rc < 0 and b"head_dim" in amb_lib.amb_last_error()
-    rc = amb_lib.amb_layernorm(None, 0, 0, None, None, None, 0, 1, 2048, 1e-5, None)
+    rc = amb_lib.amb_layernorm(None, 0, 0, None, None, None, 0, 0, 1, 2048, 1e-5, None)
     assert rc < 0
 
 
