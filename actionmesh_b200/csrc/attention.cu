@@ -113,11 +113,9 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_expect_tx(&kv_full[s], 2 * L::KV_TILE_BYTES);
         uint8_t* sk = smem + L::KV_OFF + s * 2 * L::KV_TILE_BYTES;
         uint8_t* sv = sk + L::KV_TILE_BYTES;
-        // tensor-map coordinate 3 = batch * kv_chunks + chunk  (chunks are an extra outer dimension)
-        const int c3 = batch * p.kv_chunks + chunk;
-        for (int c = 0; c < DH; ++c) {
-          tma_load_4d(sk + c * (ATT_BK * 128), &tmK, &kv_full[s], c * 64, key0, head, c3, kEvictLast);
-          tma_load_4d(sv + c * (ATT_BK * 128), &tmV, &kv_full[s], c * 64, key0, head, c3, kEvictLast);
+        for (int c = 0; c < DH; ++c) {  // K/V maps are 5-D: (d, key, head, batch, chunk)
+          tma_load_5d(sk + c * (ATT_BK * 128), &tmK, &kv_full[s], c * 64, key0, head, batch, chunk, kEvictLast);
+          tma_load_5d(sv + c * (ATT_BK * 128), &tmV, &kv_full[s], c * 64, key0, head, batch, chunk, kEvictLast);
         }
         if (++s == STAGES) { s = 0; phase ^= 1; }
       }
@@ -131,7 +129,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t sp_addr = smem_u32(smem + L::P_OFF);
       const uint32_t skv_addr = smem_u32(smem + L::KV_OFF);
 
-      auto issue_qk = [&](int i, int stage) {
+      auto issue_qk = [=](int i, int stage) {
         const uint32_t qa = sq_addr + i * L::Q_TILE_BYTES;
         const uint32_t ka = skv_addr + stage * 2 * L::KV_TILE_BYTES;
 #pragma unroll
@@ -142,7 +140,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         tc_commit(&s_full[i]);
       };
-      auto issue_pv = [&](int i, int stage, bool accumulate) {
+      auto issue_pv = [=](int i, int stage, bool accumulate) {
         const uint32_t pa = sp_addr + i * L::P_TILE_BYTES;
         const uint32_t va = skv_addr + stage * 2 * L::KV_TILE_BYTES + L::KV_TILE_BYTES;
 #pragma unroll
@@ -377,6 +375,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp >= 8) {
   if (warp == 8) {
     if (lane == 0) {
       // ===================== TMA producer =====================
@@ -390,18 +389,17 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int j = 0; j < n_kv; ++j) {
         const int chunk = j / tiles_per_chunk;
         const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
-        const int c3 = batch * p.kv_chunks + chunk;
         mbar_wait(&k_empty[ks], kph ^ 1);
         mbar_expect_tx(&k_full[ks], L::TILE_BYTES);
         uint8_t* sk = smem + L::K_OFF + ks * L::TILE_BYTES;
-        tma_load_4d(sk, &tmK, &k_full[ks], 0, key0, head, c3, kEvictLast);
-        tma_load_4d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, c3, kEvictLast);
+        tma_load_5d(sk, &tmK, &k_full[ks], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, batch, chunk, kEvictLast);
         if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(&v_empty[vs], vph ^ 1);
         mbar_expect_tx(&v_full[vs], L::TILE_BYTES);
         uint8_t* sv = smem + L::V_OFF + vs * L::TILE_BYTES;
-        tma_load_4d(sv, &tmV, &v_full[vs], 0, key0, head, c3, kEvictLast);
-        tma_load_4d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, c3, kEvictLast);
+        tma_load_5d(sv, &tmV, &v_full[vs], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, batch, chunk, kEvictLast);
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
@@ -414,7 +412,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
       const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
 
-      auto issue_qk = [&](int i, int kstage) {
+      auto issue_qk = [=](int i, int kstage) {
         const uint32_t qa = sq_addr + i * L::TILE_BYTES;
         const uint32_t ka = sk_addr + kstage * L::TILE_BYTES;
         const uint32_t d = tmem_base + i * 128;
@@ -425,7 +423,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
         tc_commit(&s_full[i]);
       };
-      auto issue_pv_half = [&](int i, int vstage, int half, bool first_tile) {
+      auto issue_pv_half = [=](int i, int vstage, int half, bool first_tile) {
         const uint32_t va = sv_addr + vstage * L::TILE_BYTES;
         const uint32_t d = tmem_base + 256 + i * 128;
         const uint32_t pa = tmem_base + i * 128;  // P aliases S_i: 16 keys = 8 columns
@@ -485,6 +483,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
+  }
   } else {
     // ===================== softmax warpgroups =====================
     const int wg = warp >> 2;
@@ -504,27 +503,25 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tc_fence_after();
       const int jj = j % tiles_per_chunk;
       const int valid = (jj == tiles_per_chunk - 1) ? last_valid : V2_BK;
-      // ---- pass 1: row max over the 128 scores
-      float mx = -INFINITY;
+      // ---- one TMEM read of the 128 scores of this row (4 back-to-back loads, one wait)
+      float sc[V2_BK];
+      tmem_ld_x32f(s_addr, sc);
+      tmem_ld_x32f(s_addr + 32, sc + 32);
+      tmem_ld_x32f(s_addr + 64, sc + 64);
+      tmem_ld_x32f(s_addr + 96, sc + 96);
+      tmem_wait_ld();
+      if (valid < V2_BK) {
 #pragma unroll
-      for (int c = 0; c < V2_BK; c += 64) {
-        float a[32], b[32];
-        tmem_ld_x32f(s_addr + c, a);
-        tmem_ld_x32f(s_addr + c + 32, b);
-        tmem_wait_ld();
-        if (valid < V2_BK) {
-#pragma unroll
-          for (int t = 0; t < 32; ++t) {
-            if (c + t >= valid) a[t] = -INFINITY;
-            if (c + 32 + t >= valid) b[t] = -INFINITY;
-          }
-        }
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          mx = fmaxf(mx, fmaxf(a[t], a[t + 1]));
-          mx = fmaxf(mx, fmaxf(b[t], b[t + 1]));
-        }
+        for (int t = 0; t < V2_BK; ++t)
+          if (t >= valid) sc[t] = -INFINITY;
       }
+      float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
+#pragma unroll
+      for (int t = 4; t < V2_BK; t += 4) {
+        mx0 = fmaxf(mx0, fmaxf(sc[t], sc[t + 1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[t + 2], sc[t + 3]));
+      }
+      const float mx = fmaxf(mx0, mx1);
       const float m_new = fmaxf(m_used, mx);
       const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
       if (j == 0) {
@@ -546,24 +543,18 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         }
         tmem_wait_st();
       }
-      // ---- pass 2: exponentials, bf16 P written over the consumed S columns
+      // ---- exponentials; bf16 P written over the consumed S columns, handed to the MMA warp in two halves
       const float mb = m_used * p.scale_log2;
-      float psum = 0.f;
+      float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float sv[32];
-        tmem_ld_x32f(s_addr + c * 32, sv);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
-          float e0 = ex2_approx(fmaf(sv[t], p.scale_log2, -mb));
-          float e1 = ex2_approx(fmaf(sv[t + 1], p.scale_log2, -mb));
-          if (valid < V2_BK) {
-            if (c * 32 + t >= valid) e0 = 0.f;
-            if (c * 32 + t + 1 >= valid) e1 = 0.f;
-          }
-          psum += e0 + e1;
+          const float e0 = ex2_approx(fmaf(sc[c * 32 + t], p.scale_log2, -mb));      // exp2(-inf) = 0 masks the tail
+          const float e1 = ex2_approx(fmaf(sc[c * 32 + t + 1], p.scale_log2, -mb));
+          ps0 += e0;
+          ps1 += e1;
           pk[t >> 1] = pack_bf16(e0, e1);
         }
         tmem_st_x16(s_addr + c * 16, pk);
@@ -576,7 +567,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_b[wg]);
-      row_sum += psum;
+      row_sum += ps0 + ps1;
     }
 
     mbar_wait(&o_full[wg], 0);
@@ -625,22 +616,15 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
     int r = encode_tmap_bf16(&tmQ, a->q, 4, dims, str, box);
     if (r) return r;
   }
-  // K/V: the outermost tensor-map coordinate enumerates (batch, chunk); with one chunk it is just the batch.
-  // Chunked K/V (frame-sharded window) needs b-stride == kv_chunks * chunk-stride so the two collapse into one dim.
+  // K/V maps are 5-D (d, key, head, batch, chunk) with free strides: one chunk per rank of a frame-sharded window
+  // (all-gather output is chunk-major), a single chunk otherwise.
   auto enc_kv = [&](CUtensorMap* tm, const void* base, int64_t ss, int64_t sh, int64_t sb, int64_t schunk) -> int {
-    int64_t outer_stride = sb;
-    if (chunks > 1) {
-      if (a->batch > 1 && sb != schunk * chunks) {
-        set_last_error("flash_attn: kv_chunks > 1 requires b-stride == kv_chunks * chunk-stride (got %lld vs %lld)",
-                       (long long)sb, (long long)(schunk * chunks));
-        return AMB_ERR_UNSUPPORTED;
-      }
-      outer_stride = schunk;
-    }
-    uint64_t dims[4] = {(uint64_t)D, (uint64_t)sk_chunk, (uint64_t)a->heads, (uint64_t)a->batch * chunks};
-    uint64_t str[3] = {(uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)outer_stride * 2};
-    uint32_t box[4] = {64, BKV, 1, 1};
-    return encode_tmap_bf16(tm, base, 4, dims, str, box);
+    if (chunks == 1) schunk = sb > 0 ? sb : 16;  // extent-1 dimension: any legal stride
+    uint64_t dims[5] = {(uint64_t)D, (uint64_t)sk_chunk, (uint64_t)a->heads, (uint64_t)a->batch, (uint64_t)chunks};
+    uint64_t str[4] = {(uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)sb * 2, (uint64_t)schunk * 2};
+    if (a->batch == 1 && str[2] == 0) str[2] = str[0] * sk_chunk;
+    uint32_t box[5] = {64, BKV, 1, 1, 1};
+    return encode_tmap_bf16(tm, base, 5, dims, str, box);
   };
   int r = enc_kv(&tmK, a->k, a->k_stride_s, a->k_stride_h, a->k_stride_b, a->k_chunk_stride);
   if (r) return r;

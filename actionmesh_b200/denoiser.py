@@ -232,8 +232,8 @@ class B200Denoiser:
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ workspaces
-    def _workspace(self, B: int, T: int, N: int) -> dict:
-        key = (B, T, N)
+    def _workspace(self, B: int, T: int, N: int, world: int = 1) -> dict:
+        key = (B, T, N, world)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -256,23 +256,32 @@ class B200Denoiser:
             "skips": [torch.empty(M, c.width, dtype=bf, device=dev) for _ in range(n_skips)],
             "pred": torch.empty(M, c.in_channels, dtype=bf, device=dev),
         }
+        if world > 1:  # frame-sharded window: local [K|V] rows and the all-gathered buffer (one chunk per rank)
+            ws["kv_local"] = torch.empty(M, 2 * c.width, dtype=bf, device=dev)
+            ws["kv_all"] = torch.empty(world, M, 2 * c.width, dtype=bf, device=dev)
         self._ws = {key: ws}  # keep one shape resident
         return ws
 
     # ------------------------------------------------------------------ per-window cache
-    def precompute_window(self, context: torch.Tensor, framestep: torch.Tensor, N: int) -> WindowState:
+    def precompute_window(self, context: torch.Tensor, framestep: torch.Tensor, N: int,
+                          frame_slice: Optional[slice] = None) -> WindowState:
         """Step-invariant work of one AR window: RoPE tables (temporal_denoiser.py:114-149) and, for every layer,
         K = norm_k(to_k(ctx)), V = to_v(ctx) of the cross-attention (attention_processor.py:101-124).  Batch elements
         whose context is identically zero (the CFG "no image" branch, guidance.py:73) are flagged so their
         cross-attention collapses to `to_out.0.bias`; that check is the only host sync, once per window."""
         c = self.config
         dev = self._device
+        # RoPE: theta_j = 10000^(-2j/d_h); phase = (framestep - min) * theta_j   (rotary_embedding.py:42-58).  With a
+        # frame-sharded window the minimum is taken over the WHOLE window, then this rank's frames are selected.
+        fs = framestep.detach().to("cpu", torch.float32)
+        pos = fs - fs.min(dim=1, keepdim=True).values
+        if frame_slice is not None:
+            pos = pos[:, frame_slice]
+            context = context[:, frame_slice]
         B, T, S, Dc = context.shape
         st = WindowState()
         st.shape = (B, T, N)
-        # RoPE: theta_j = 10000^(-2j/d_h); phase = (framestep - min) * theta_j   (rotary_embedding.py:42-58)
-        fs = framestep.detach().to("cpu", torch.float32)
-        pos = (fs - fs.min(dim=1, keepdim=True).values).reshape(B * T)
+        pos = pos.reshape(B * T)
         inv = 1.0 / (10000.0 ** (torch.arange(0, c.head_dim, 2, dtype=torch.float32) / c.head_dim))
         ph = torch.outer(pos, inv)
         st.rope_cos = ph.cos().to(dev).contiguous()
@@ -314,7 +323,7 @@ class B200Denoiser:
     __call__ = forward
 
     def _forward_packed(self, ws: dict, st: WindowState, B: int, T: int, N: int, t32: torch.Tensor,
-                        m32: Optional[torch.Tensor], n_input_branches: int) -> torch.Tensor:
+                        m32: Optional[torch.Tensor], n_input_branches: int, shard=None) -> torch.Tensor:
         """Runs the 21-block DiT on ws['x_in'] (bf16 latents of `n_input_branches` batch elements; when fewer than B,
         the same latents feed every CFG branch) and leaves the prediction in ws['pred'] (M, C) bf16."""
         c = self.config
@@ -352,17 +361,33 @@ class B200Denoiser:
                 h_in = h
             # ---- self-attention (block.py:137-142, attention_processor.py:49-166)
             ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
-            ops.gemm(xn, w[p + "s.qkv"], qkv,
-                     norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
-                               cos=st.rope_cos, sin=st.rope_sin, rows_per_pos=L))
-            if i in c.inflated_layers:
-                view = (B, T * L, H, dh)
+            inflated = i in c.inflated_layers
+            if shard is not None and shard.world > 1 and inflated:
+                # frame-sharded window: K/V of this rank's frames -> NCCL all-gather -> attention over `world` chunks;
+                # the Q projection runs while the gather is in flight.
+                from .window_shard import chunked_kv_views
+                import torch.distributed as dist
+                kv_local, kv_all = ws["kv_local"], ws["kv_all"]
+                ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
+                         norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
+                                   sin=st.rope_sin, rows_per_pos=L))
+                work = dist.all_gather_into_tensor(kv_all.view(-1, 2 * D), kv_local, group=shard.group, async_op=True)
+                ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
+                         norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
+                                   sin=st.rope_sin, rows_per_pos=L))
+                work.wait()
+                k5, v5 = chunked_kv_views(kv_all, B, T * L, H, dh)
+                q4 = qkv[:, 0:D].unflatten(0, (B, T * L)).unflatten(-1, (H, dh))
+                ops.flash_attn(q4, k5, v5, att.view(B, T * L, H, dh), scale, kv_chunks=shard.world, tag="attn_self")
             else:
-                view = (B * T, L, H, dh)
-            q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-            k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-            v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-            ops.flash_attn(q4, k4, v4, att.view(*view), scale, tag="attn_self")
+                ops.gemm(xn, w[p + "s.qkv"], qkv,
+                         norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
+                                   cos=st.rope_cos, sin=st.rope_sin, rows_per_pos=L))
+                view = (B, T * L, H, dh) if inflated else (B * T, L, H, dh)
+                q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+                k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+                v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+                ops.flash_attn(q4, k4, v4, att.view(*view), scale, tag="attn_self")
             ops.gemm(att, w[p + "s.o.w"], h, bias=w[p + "s.o.b"], residual=h_in)
             h_in = h
             # ---- cross-attention (block.py:146-149); zero-context batch elements reduce to + to_out.0.bias (A.5)

@@ -82,15 +82,25 @@ class B200SchedulerFlow:
     def denoise(self, diffusion_model, cf_guidance: ClassifierFreeGuidance, init_latent: torch.Tensor,
                 context: torch.Tensor, device="cuda:0", disable_prog: bool = True,
                 mask: Optional[torch.Tensor] = None, framestep: Optional[torch.Tensor] = None,
-                step_callback: Optional[Callable] = None) -> torch.Tensor:
+                step_callback: Optional[Callable] = None, shard=None) -> torch.Tensor:
         """Same contract as SchedulerFlow.denoise (scheduler.py:253-295): returns the denoised latents; `init_latent`
-        is updated in place on unobserved frames and observed frames stay bit-identical."""
+        is updated in place on unobserved frames and observed frames stay bit-identical.
+
+        `shard` (window_shard.FrameShard, optional extension): every rank calls denoise() with the SAME full-window
+        arguments; each rank denoises its own frames (K/V all-gathered per layer) and the result is all-gathered."""
         if not isinstance(diffusion_model, B200Denoiser):
             raise AmbError("B200SchedulerFlow.denoise drives a B200Denoiser (no CPU / generic-module fallback)")
         model = diffusion_model
         if init_latent.dtype != torch.float32 or not init_latent.is_cuda:
             raise AmbError("init_latent must be an fp32 CUDA tensor")
         latents = init_latent if init_latent.is_contiguous() else init_latent.contiguous()
+        if mask is not None and not bool((mask == 0).any()):  # scheduler.py:245 asserts this every step; once is enough
+            raise AssertionError("No unobserved frames found")
+        fsl = None
+        if shard is not None and shard.world > 1:
+            fsl = shard.frames(latents.shape[1])
+            latents = latents[:, fsl].contiguous()
+            mask = None if mask is None else mask.reshape(init_latent.shape[0], -1)[:, fsl]
         B, T, N, C = latents.shape
         timesteps, distances = self.get_schedule()
         branches = cf_guidance.branches()
@@ -101,9 +111,9 @@ class B200SchedulerFlow:
         # ---- per-window, step-invariant state
         ctx = context.to(device=dev, dtype=torch.float32)
         ctx_all = torch.cat([ctx if ui else torch.zeros_like(ctx) for ui, _ in branches], dim=0)  # once per window
-        fs = framestep if framestep is not None else torch.zeros(B, T)
+        fs = framestep if framestep is not None else torch.zeros(B, ctx.shape[1])
         fs_all = torch.cat([fs] * K, dim=0)
-        state: WindowState = model.precompute_window(ctx_all, fs_all, N)
+        state: WindowState = model.precompute_window(ctx_all, fs_all, N, frame_slice=fsl)
         del ctx_all
         m32 = None
         upd = torch.ones(B * T, dtype=torch.uint8, device=dev)
@@ -111,19 +121,20 @@ class B200SchedulerFlow:
             mk = mask.to(device=dev, dtype=torch.float32).reshape(B, T)
             m32 = torch.cat([mk if ul else torch.zeros_like(mk) for _, ul in branches], dim=0).reshape(K * B * T).contiguous()
             upd = (mk.reshape(B * T) == 0).to(torch.uint8)
-            if not bool(upd.any()):  # scheduler.py:245 asserts this every step; once per window is enough
-                raise AssertionError("No unobserved frames found")
-        ws = model._workspace(K * B, T, N)
+        ws = model._workspace(K * B, T, N, world=shard.world if fsl is not None else 1)
         L = N + 1
         sign = 1.0 if self.is_additive else -1.0
         t_dev = timesteps.to(dev)
         for i in range(self.num_inference_steps):
             ops.cast_bf16(latents.view(B * T * N, C), out=ws["x_in"][: B * T * N])
-            pred = model._forward_packed(ws, state, K * B, T, N, t_dev[i:i + 1], m32, n_input_branches=B)
+            pred = model._forward_packed(ws, state, K * B, T, N, t_dev[i:i + 1], m32, n_input_branches=B,
+                                         shard=shard if fsl is not None else None)
             ops.cfg_euler_step(latents, pred, scales, sign * float(distances[i]), upd, n_branches=K,
                                branch_stride=B * T * L * C, frame_stride=L * C, frame_offset=C, n_per_frame=N * C)
             if step_callback is not None:
                 step_callback(i + 1, self.num_inference_steps)
-        if latents.data_ptr() != init_latent.data_ptr():
+        if fsl is not None:
+            init_latent.copy_(shard.gather_latents(latents))  # once per window; observed frames come back unchanged
+        elif latents.data_ptr() != init_latent.data_ptr():
             init_latent.copy_(latents)
         return init_latent

@@ -1,0 +1,123 @@
+"""Temporal (frame) sharding of ONE 16-frame denoising window across the GPUs of a box.
+
+Everything in a DiT block is token-local — LayerNorm, QKV / out / MLP GEMMs, the cross-attention to the frame's own 257
+context tokens (temporal_denoiser.py:221-226), the skip linears, the time token — except the inflated self-attention,
+where every query attends to the keys of all T·L tokens (attention_processor.py:49-65).  So each rank owns T/world
+consecutive frames of every CFG branch, keeps its queries local, and per layer all-gathers K and V (post RMSNorm/RoPE,
+bf16) over NCCL.  The attention kernel consumes the gathered buffer in place as `kv_chunks = world` chunks (5-D TMA map
+with a free chunk stride; no re-layout).  The fp32 latents are sharded the same way and all-gathered once per window.
+
+One process per GPU (`torch.distributed`, backend "nccl" on the box, "gloo" in the CPU tests of the index logic).
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+
+def frame_partition(n_frames: int, world: int, rank: int) -> slice:
+    """Frames [rank*T/world, (rank+1)*T/world).  T must divide evenly (16 frames over 1/2/4/8 ranks)."""
+    if n_frames % world:
+        raise ValueError(f"{n_frames} frames do not shard evenly over {world} ranks")
+    per = n_frames // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def gather_kv(kv_local: torch.Tensor, group=None) -> torch.Tensor:
+    """All-gather the local (B*T_local*L, 2D) [K|V] rows of one layer -> (world, B*T_local*L, 2D), rank-major."""
+    world = dist.get_world_size(group)
+    out = torch.empty((world,) + tuple(kv_local.shape), dtype=kv_local.dtype, device=kv_local.device)
+    dist.all_gather_into_tensor(out.view(-1, kv_local.shape[-1]), kv_local.contiguous(), group=group)  # concat along dim 0
+    return out
+
+
+def chunked_kv_views(kv_all: torch.Tensor, B: int, s_local: int, H: int, dh: int):
+    """(world, B*s_local, 2*H*dh) gathered buffer -> K, V views of logical shape (B, world, s_local, H, dh): chunk c of
+    batch b is rank c's keys; concatenating the chunks in rank order restores the window's frame order."""
+    world = kv_all.shape[0]
+    D = H * dh
+    kv5 = kv_all.view(world, B, s_local, 2 * D).permute(1, 0, 2, 3)  # (B, world, s_local, 2D), no copy
+    k = kv5[..., 0:D].unflatten(-1, (H, dh))
+    v = kv5[..., D:2 * D].unflatten(-1, (H, dh))
+    return k, v
+
+
+class FrameShard:
+    """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def frames(self, n_frames: int) -> slice:
+        return frame_partition(n_frames, self.world, self.rank)
+
+    def gather_latents(self, local: torch.Tensor) -> torch.Tensor:
+        """(1, T_local, N, C) fp32 per rank -> (1, T, N, C) on every rank (once per window)."""
+        out = torch.empty((self.world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out.view(-1, *local.shape[2:]), local[0].contiguous(), group=self.group)
+        return out.reshape(1, -1, *local.shape[2:])
+
+
+def run_temporal_bench(args, rank: int, local: int, world: int):
+    """bench.py --mode temporal: ONE default window, frames sharded over `world` ranks (strong scaling)."""
+    import json
+
+    from . import ops
+    from .denoiser import B200Denoiser, DenoiserConfig
+    from .guidance import ClassifierFreeGuidance
+    from .scheduler import B200SchedulerFlow
+
+    dev = torch.device("cuda", local)
+    K, W = args.steps, max(args.warmup, 0)
+    T, N, C, S, Dc = 16, 2048, 64, 257, 1024
+    shard = FrameShard()
+    model = B200Denoiser(DenoiserConfig()).to(dev)
+    model.init_random_(seed=1234)  # same seed on every rank => replicated weights
+    cf = ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
+    g = torch.Generator(device="cpu").manual_seed(44)
+    lat = torch.randn(1, T, N, C, generator=g).to(dev)
+    ctx = torch.randn(1, T, S, Dc, generator=torch.Generator().manual_seed(5)).to(dev)
+    mask = torch.zeros(1, T, device=dev)
+    mask[0, 0] = 1.0
+    framestep = torch.arange(T, dtype=torch.float32)[None]
+    sch = B200SchedulerFlow(num_inference_steps=W + K, shift=3.0, is_additive=True)
+    ev = {}
+    marks = {"l0": 0}
+
+    def cb(step, total):
+        if step == W:
+            ev["t0"] = torch.cuda.Event(enable_timing=True)
+            ev["t0"].record()
+            marks["l0"] = ops.launch_count
+        if step == total:
+            ev["t1"] = torch.cuda.Event(enable_timing=True)
+            ev["t1"].record()
+
+    dist.barrier()
+    torch.cuda.synchronize()
+    if W == 0:
+        cb(0, W + K)
+    sch.denoise(model, cf, lat, ctx, device=dev, mask=mask, framestep=framestep, step_callback=cb, shard=shard)
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([ev["t0"].elapsed_time(ev["t1"])], device=dev, dtype=torch.float64)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    if rank == 0:
+        from bench import F_STEP, METRIC, UNIT, WORKLOAD  # type: ignore
+
+        line = {
+            "metric": METRIC, "value": K / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"temporal-shard x{world} (frames/rank {T // world}), "
+                       "K/V all-gather per layer over NCCL", "l2": "inputs larger than L2"},
+            "step_flops": F_STEP, "gpu_launches": ops.launch_count - marks["l0"],
+        }
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()

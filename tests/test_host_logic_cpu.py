@@ -57,3 +57,22 @@ def test_qkv_repack_equals_head_interleaved_split():
     packed = c @ repack_cross_kv(wk2, wv2, H).t()
     assert torch.allclose(packed[:, :D].view(7, H, dh), k_ref, atol=1e-5)
     assert torch.allclose(packed[:, D:].view(7, H, dh), v_ref, atol=1e-5)
+
+
+def test_windows_and_bank_match_reference_known_answers():
+    from actionmesh_b200.windows import LatentBank, chunk_from
+
+    host = load_golden("host_logic.pt")
+    for args, ref in host["chunk_from"].items():
+        got = chunk_from(*args)
+        assert len(got) == len(ref) and all(torch.equal(a, b) for a, b in zip(got, ref)), args
+    bank = LatentBank(empty_dims=(4, 2))
+    bank.update(torch.tensor([3.0]), torch.ones(1, 4, 2))
+    bank.update(torch.tensor([3.0]), torch.zeros(1, 4, 2))  # no overwrite unless replace=True (storage.py:62-71)
+    lat, msk = bank.get(torch.tensor([2.0, 3.0, 4.0]), "cpu", add_batch_dim=True)
+    assert torch.equal(lat, host["bank_get"][0]) and torch.equal(msk, host["bank_get"][1])
+    bank.update(torch.tensor([3.0]), torch.zeros(1, 4, 2), replace=True)
+    assert float(bank.get(torch.tensor([3.0]), "cpu")[0].abs().sum()) == 0.0
+    bank.update(torch.tensor([1.0]), torch.full((1, 4, 2), 2.0))
+    lat, ts = bank.get_ordered()
+    assert ts.tolist() == [1.0, 3.0] and float(lat[0, 0, 0]) == 2.0
