@@ -58,7 +58,7 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   uint64_t* o_full = p_ready + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath for role code)
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * ATT_BQ);
   const int head = blockIdx.y;
@@ -93,23 +93,24 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s[2] = {tmem_base, tmem_base + 64};
-  const uint32_t tmem_o[2] = {tmem_base + 128, tmem_base + 128 + D};
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer (warp converged, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * L::Q_TILE_BYTES);
       for (int i = 0; i < 2; ++i)
         for (int c = 0; c < DH; ++c)
           tma_load_4d(smem + L::Q_OFF + i * L::Q_TILE_BYTES + c * (ATT_BQ * 128), &tmQ, q_full, c * 64,
                       q0 + i * ATT_BQ, head, batch, kEvictFirst);
-      int s = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int chunk = j / tiles_per_chunk;
-        const int key0 = (j - chunk * tiles_per_chunk) * ATT_BK;
-        mbar_wait(&kv_empty[s], phase ^ 1);
+    }
+    __syncwarp();
+    int s = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const int chunk = j / tiles_per_chunk;
+      const int key0 = (j - chunk * tiles_per_chunk) * ATT_BK;
+      mbar_wait(&kv_empty[s], phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&kv_full[s], 2 * L::KV_TILE_BYTES);
         uint8_t* sk = smem + L::KV_OFF + s * 2 * L::KV_TILE_BYTES;
         uint8_t* sv = sk + L::KV_TILE_BYTES;
@@ -117,81 +118,91 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           tma_load_5d(sk + c * (ATT_BK * 128), &tmK, &kv_full[s], c * 64, key0, head, batch, chunk, kEvictLast);
           tma_load_5d(sv + c * (ATT_BK * 128), &tmV, &kv_full[s], c * 64, key0, head, batch, chunk, kEvictLast);
         }
-        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);  // S[128 x 64]  = Q (K-major) · K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);      // O[128 x D]  += P (K-major) · V (MN-major)
-      const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
-      const uint32_t sp_addr = smem_u32(smem + L::P_OFF);
-      const uint32_t skv_addr = smem_u32(smem + L::KV_OFF);
+    // ===================== MMA issuer (warp converged; descriptors stay in uniform registers) =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, ATT_BK, 0, 0);  // S[128 x 64]  = Q (K-major) · K (K-major)
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);      // O[128 x D]  += P (K-major) · V (MN-major)
+    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+    const uint32_t sp_addr = smem_u32(smem + L::P_OFF);
+    const uint32_t skv_addr = smem_u32(smem + L::KV_OFF);
+    const uint32_t ts0 = tmem_base, ts1 = tmem_base + 64, to0 = tmem_base + 128, to1 = tmem_base + 128 + D;
 
-      auto issue_qk = [=](int i, int stage) {
-        const uint32_t qa = sq_addr + i * L::Q_TILE_BYTES;
-        const uint32_t ka = skv_addr + stage * 2 * L::KV_TILE_BYTES;
+    auto issue_qk = [=](int i, int stage) {
+      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::Q_TILE_BYTES);
+      const uint64_t kd = make_desc_kmajor_sw128(skv_addr + stage * 2 * L::KV_TILE_BYTES);
+      const uint32_t d = i ? ts1 : ts0;
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t half = k >> 2, ko = (k & 3) * 32;
-          mma_ss(tmem_s[i], make_desc_kmajor_sw128(qa + half * (ATT_BQ * 128) + ko),
-                 make_desc_kmajor_sw128(ka + half * (ATT_BK * 128) + ko), idesc_qk, k != 0);
-        }
+        for (int k = 0; k < D / 16; ++k)  // descriptor address field is (bytes >> 4)
+          mma_ss(d, qd + ((k >> 2) * (ATT_BQ * 128 / 16) + (k & 3) * 2), kd + ((k >> 2) * (ATT_BK * 128 / 16) + (k & 3) * 2),
+                 idesc_qk, k != 0);
         tc_commit(&s_full[i]);
-      };
-      auto issue_pv = [=](int i, int stage, bool accumulate) {
-        const uint32_t pa = sp_addr + i * L::P_TILE_BYTES;
-        const uint32_t va = skv_addr + stage * 2 * L::KV_TILE_BYTES + L::KV_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < ATT_BK / 16; ++k) {
-          // V tile: [64 keys][64 d] boxes of 128-B rows; 16 keys = 2048 B; next 64 d-columns ATT_BK*128 B further
-          mma_ss(tmem_o[i], make_desc_kmajor_sw128(pa + k * 32),
-                 make_desc_mnmajor_sw128(va + k * 2048, ATT_BK * 128), idesc_pv, (accumulate || k != 0) ? 1u : 0u);
-        }
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      int s = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        int s_next = s + 1;
-        uint32_t phase_next = phase;
-        if (s_next == STAGES) { s_next = 0; phase_next ^= 1; }
-        const bool has_next = (j + 1 < n_kv);
-        // ---- tile 0
-        mbar_wait(&p_ready[0], j & 1);
-        tc_fence_after();
-        issue_pv(0, s, j > 0);
-        if (has_next) {
-          mbar_wait(&kv_full[s_next], phase_next);
-          tc_fence_after();
-          issue_qk(0, s_next);
-        } else {
-          tc_commit(&o_full[0]);
-        }
-        // ---- tile 1
-        mbar_wait(&p_ready[1], j & 1);
-        tc_fence_after();
-        issue_pv(1, s, j > 0);
-        tc_commit(&kv_empty[s]);  // K_j and V_j fully consumed once everything issued so far has completed
-        if (has_next) {
-          issue_qk(1, s_next);
-        } else {
-          tc_commit(&o_full[1]);
-        }
-        s = s_next;
-        phase = phase_next;
       }
+      __syncwarp();
+    };
+    auto issue_pv = [=](int i, int stage, bool accumulate) {
+      const uint64_t pd = make_desc_kmajor_sw128(sp_addr + i * L::P_TILE_BYTES);
+      // V tile: [64 keys][64 d] boxes of 128-B rows; 16 keys = 2048 B; next 64 d-columns ATT_BK*128 B further
+      const uint64_t vd = make_desc_mnmajor_sw128(skv_addr + stage * 2 * L::KV_TILE_BYTES + L::KV_TILE_BYTES, ATT_BK * 128);
+      const uint32_t d = i ? to1 : to0;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < ATT_BK / 16; ++k)
+          mma_ss(d, pd + 2 * k, vd + 128 * k, idesc_pv, (accumulate || k != 0) ? 1u : 0u);
+      }
+      __syncwarp();
+    };
+    auto commit = [=](uint64_t* bar) {
+      if (elect_one()) tc_commit(bar);
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    mbar_wait(&kv_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      int s_next = s + 1;
+      uint32_t phase_next = phase;
+      if (s_next == STAGES) { s_next = 0; phase_next ^= 1; }
+      const bool has_next = (j + 1 < n_kv);
+      // ---- tile 0
+      mbar_wait(&p_ready[0], j & 1);
+      tc_fence_after();
+      issue_pv(0, s, j > 0);
+      if (has_next) {
+        mbar_wait(&kv_full[s_next], phase_next);
+        tc_fence_after();
+        issue_qk(0, s_next);
+      } else {
+        commit(&o_full[0]);
+      }
+      // ---- tile 1
+      mbar_wait(&p_ready[1], j & 1);
+      tc_fence_after();
+      issue_pv(1, s, j > 0);
+      commit(&kv_empty[s]);  // K_j and V_j fully consumed once everything issued so far has completed
+      if (has_next) {
+        issue_qk(1, s_next);
+      } else {
+        commit(&o_full[1]);
+      }
+      s = s_next;
+      phase = phase_next;
     }
   } else {
     // ===================== softmax warpgroups =====================
     const int wg = (warp - 2) >> 2;       // 0 or 1: which query tile
     const int quarter = warp & 3;         // TMEM lane quarter accessible to this warp
+    const uint32_t tmem_s[2] = {tmem_base, tmem_base + 64};
+    const uint32_t tmem_o[2] = {tmem_base + 128, tmem_base + 128 + D};
     const int row_in_tile = quarter * 32 + lane;
     const int q_row = q0 + wg * ATT_BQ + row_in_tile;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
@@ -321,7 +332,7 @@ struct AttnV2Smem {
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int KSTAGES, int VSTAGES>
+template <int KSTAGES, int VSTAGES, int EMU>  // EMU: every EMU-th pair of exponentials runs on the FMA pipes (0 = none)
 __global__ void __launch_bounds__(V2_THREADS, 1)
 flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -340,7 +351,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   uint64_t* o_full = p_b + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath for role code)
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * (2 * ATT_BQ);
   const int head = blockIdx.y;
@@ -377,111 +388,125 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 
   if (warp >= 8) {
   if (warp == 8) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
+    // ===================== TMA producer (warp converged, one elected lane issues) =====================
+    if (elect_one()) {
       mbar_expect_tx(q_full, 2 * L::TILE_BYTES);
       for (int i = 0; i < 2; ++i)
         for (int c = 0; c < 2; ++c)
           tma_load_4d(smem + L::Q_OFF + i * L::TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
                       batch, kEvictFirst);
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        const int chunk = j / tiles_per_chunk;
-        const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
-        mbar_wait(&k_empty[ks], kph ^ 1);
+    }
+    __syncwarp();
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const int chunk = j / tiles_per_chunk;
+      const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
+      mbar_wait(&k_empty[ks], kph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&k_full[ks], L::TILE_BYTES);
         uint8_t* sk = smem + L::K_OFF + ks * L::TILE_BYTES;
         tma_load_5d(sk, &tmK, &k_full[ks], 0, key0, head, batch, chunk, kEvictLast);
         tma_load_5d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, batch, chunk, kEvictLast);
-        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-        mbar_wait(&v_empty[vs], vph ^ 1);
+      }
+      __syncwarp();
+      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+      mbar_wait(&v_empty[vs], vph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(&v_full[vs], L::TILE_BYTES);
         uint8_t* sv = smem + L::V_OFF + vs * L::TILE_BYTES;
         tma_load_5d(sv, &tmV, &v_full[vs], 0, key0, head, batch, chunk, kEvictLast);
         tma_load_5d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, batch, chunk, kEvictLast);
-        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
+      __syncwarp();
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
     }
   } else if (warp == 9) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V2_BK, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
-      const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
-      const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
-      const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
+    // ===================== MMA issuer (warp converged; descriptors stay in uniform registers) =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V2_BK, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
+    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
+    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
 
-      auto issue_qk = [=](int i, int kstage) {
-        const uint32_t qa = sq_addr + i * L::TILE_BYTES;
-        const uint32_t ka = sk_addr + kstage * L::TILE_BYTES;
-        const uint32_t d = tmem_base + i * 128;
+    auto issue_qk = [=](int i, int kstage) {
+      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::TILE_BYTES);
+      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::TILE_BYTES);
+      const uint32_t d = tmem_base + i * 128;
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * 16384 + (k & 3) * 32;
-          mma_ss(d, make_desc_kmajor_sw128(qa + off), make_desc_kmajor_sw128(ka + off), idesc_qk, k != 0);
+          const uint32_t off = (k >> 2) * (16384 / 16) + (k & 3) * 2;  // descriptor address field is (bytes >> 4)
+          mma_ss(d, qd + off, kd + off, idesc_qk, k != 0);
         }
         tc_commit(&s_full[i]);
-      };
-      auto issue_pv_half = [=](int i, int vstage, int half, bool first_tile) {
-        const uint32_t va = sv_addr + vstage * L::TILE_BYTES;
-        const uint32_t d = tmem_base + 256 + i * 128;
-        const uint32_t pa = tmem_base + i * 128;  // P aliases S_i: 16 keys = 8 columns
+      }
+      __syncwarp();
+    };
+    auto issue_pv_half = [=](int i, int vstage, int half, bool first_tile) {
+      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::TILE_BYTES, 16384);
+      const uint32_t d = tmem_base + 256 + i * 128;
+      const uint32_t pa = tmem_base + i * 128;  // P aliases S_i: 16 keys = 8 columns
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const int k = half * 4 + kk;
-          mma_ts(d, pa + k * 8, make_desc_mnmajor_sw128(va + k * 2048, 16384), idesc_pv,
-                 (!first_tile || k != 0) ? 1u : 0u);
+          mma_ts(d, pa + k * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);  // 16 keys = 2048 B
         }
-      };
-
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      tc_commit(&k_empty[0]);
-      int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
-      for (int j = 0; j < n_kv; ++j) {
-        int ks_next = ks + 1;
-        uint32_t kph_next = kph;
-        if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
-        const bool has_next = (j + 1 < n_kv);
-        const uint32_t par = j & 1;
-        mbar_wait(&v_full[vs], vph);
-        // ---- tile 0
-        mbar_wait(&p_a[0], par);
-        tc_fence_after();
-        issue_pv_half(0, vs, 0, j == 0);
-        mbar_wait(&p_b[0], par);
-        tc_fence_after();
-        issue_pv_half(0, vs, 1, j == 0);
-        if (has_next) {
-          mbar_wait(&k_full[ks_next], kph_next);
-          tc_fence_after();
-          issue_qk(0, ks_next);
-        } else {
-          tc_commit(&o_full[0]);
-        }
-        // ---- tile 1
-        mbar_wait(&p_a[1], par);
-        tc_fence_after();
-        issue_pv_half(1, vs, 0, j == 0);
-        mbar_wait(&p_b[1], par);
-        tc_fence_after();
-        issue_pv_half(1, vs, 1, j == 0);
-        tc_commit(&v_empty[vs]);
-        if (has_next) {
-          issue_qk(1, ks_next);
-          tc_commit(&k_empty[ks_next]);
-        } else {
-          tc_commit(&o_full[1]);
-        }
-        ks = ks_next;
-        kph = kph_next;
-        if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
       }
+      __syncwarp();
+    };
+    auto commit = [=](uint64_t* bar) {
+      if (elect_one()) tc_commit(bar);
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    commit(&k_empty[0]);
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      int ks_next = ks + 1;
+      uint32_t kph_next = kph;
+      if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
+      const bool has_next = (j + 1 < n_kv);
+      const uint32_t par = j & 1;
+      mbar_wait(&v_full[vs], vph);
+      // ---- tile 0
+      mbar_wait(&p_a[0], par);
+      tc_fence_after();
+      issue_pv_half(0, vs, 0, j == 0);
+      mbar_wait(&p_b[0], par);
+      tc_fence_after();
+      issue_pv_half(0, vs, 1, j == 0);
+      if (has_next) {
+        mbar_wait(&k_full[ks_next], kph_next);
+        tc_fence_after();
+        issue_qk(0, ks_next);
+      } else {
+        commit(&o_full[0]);
+      }
+      // ---- tile 1
+      mbar_wait(&p_a[1], par);
+      tc_fence_after();
+      issue_pv_half(1, vs, 0, j == 0);
+      mbar_wait(&p_b[1], par);
+      tc_fence_after();
+      issue_pv_half(1, vs, 1, j == 0);
+      commit(&v_empty[vs]);
+      if (has_next) {
+        issue_qk(1, ks_next);
+        commit(&k_empty[ks_next]);
+      } else {
+        commit(&o_full[1]);
+      }
+      ks = ks_next;
+      kph = kph_next;
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
     }
   }
   } else {
@@ -545,16 +570,22 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       }
       // ---- exponentials; bf16 P written over the consumed S columns, handed to the MMA warp in two halves
       const float mb = m_used * p.scale_log2;
-      float ps0 = 0.f, ps1 = 0.f;
+      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
+      uint64_t psum2 = pk2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 32; t += 2) {
-          const float e0 = ex2_approx(fmaf(sc[c * 32 + t], p.scale_log2, -mb));      // exp2(-inf) = 0 masks the tail
-          const float e1 = ex2_approx(fmaf(sc[c * 32 + t + 1], p.scale_log2, -mb));
-          ps0 += e0;
-          ps1 += e1;
+          float x0, x1, e0, e1;
+          upk2(fma2(pk2(sc[c * 32 + t], sc[c * 32 + t + 1]), scale2, nmb2), x0, x1);
+          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+            exp2_poly2(x0, x1, e0, e1);
+          } else {
+            e0 = ex2_approx(x0);  // exp2(-inf) = 0 masks the tail
+            e1 = ex2_approx(x1);
+          }
+          psum2 = add2(psum2, pk2(e0, e1));
           pk[t >> 1] = pack_bf16(e0, e1);
         }
         tmem_st_x16(s_addr + c * 16, pk);
@@ -567,7 +598,11 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_b[wg]);
-      row_sum += ps0 + ps1;
+      {
+        float s0, s1;
+        upk2(psum2, s0, s1);
+        row_sum += s0 + s1;
+      }
     }
 
     mbar_wait(&o_full[wg], 0);
@@ -601,10 +636,332 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
 }
 
-template <int D, int STAGES, bool V2>
+
+// =====================================================================================================================
+// v3 (head_dim 128): 64-key granularity with DOUBLE-BUFFERED S per query tile.  The QK^T of key tile j+2 is issued as
+// soon as P·V of tile j has been issued, so a softmax warpgroup always finds its next S tile ready (it never waits on
+// the tensor pipe) and the tensor pipe always has two S tiles of slack per query tile.  P (bf16) aliases its S buffer.
+// TMEM: S[i][b] = columns (2i+b)*64 (+64),  O[i] = 256 + 128 i.       i = query tile, b = j & 1.
+// Tensor-pipe order: S00 S10 S01 S11 | PV0(0) S0(2) PV1(0) S1(2) | PV0(1) S0(3) PV1(1) S1(3) | ...
+// =====================================================================================================================
+constexpr int V3_BK = 64;
+constexpr int V3_THREADS = 320;
+
+template <int KSTAGES, int VSTAGES>
+struct AttnV3Smem {
+  static constexpr int Q_TILE_BYTES = 128 * 128 * 2;   // 32 KB
+  static constexpr int KV_TILE_BYTES = V3_BK * 128 * 2;  // 16 KB: two d-halves of [64 keys x 128 B]
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = 2 * Q_TILE_BYTES;
+  static constexpr int V_OFF = K_OFF + KSTAGES * KV_TILE_BYTES;
+  static constexpr int BAR_OFF = V_OFF + VSTAGES * KV_TILE_BYTES;
+  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 4 + 4 + 2 + 2;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int KSTAGES, int VSTAGES, int EMU>
+__global__ void __launch_bounds__(V3_THREADS, 1)
+flash_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnV3Smem<KSTAGES, VSTAGES>;
+  constexpr int D = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + KSTAGES;
+  uint64_t* v_full = k_empty + KSTAGES;
+  uint64_t* v_empty = v_full + VSTAGES;
+  uint64_t* s_full = v_empty + VSTAGES;  // [tile][buf] -> index 2*tile + buf
+  uint64_t* p_ready = s_full + 4;        // [tile][buf]
+  uint64_t* pv_done = p_ready + 4;       // [tile]: completes once per P·V (guards the rare O rescale)
+  uint64_t* o_full = pv_done + 2;        // [tile]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath for role code)
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int tiles_per_chunk = (p.sk_chunk + V3_BK - 1) / V3_BK;
+  const int n_kv = p.kv_chunks * tiles_per_chunk;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 9) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+      for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
+      for (int i = 0; i < 2; ++i) { mbar_init(&pv_done[i], 1); mbar_init(&o_full[i], 1); }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ===================== TMA producer (warp converged, one elected lane issues) =====================
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * L::Q_TILE_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d(smem + L::Q_OFF + i * L::Q_TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
+                      batch, kEvictFirst);
+    }
+    __syncwarp();
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    // K runs two tiles ahead of V (the QK^T look-ahead); issue order K0 K1 | V0 K2 | V1 K3 | ...
+    // (lambdas capture POINTERS to the __grid_constant__ tensor maps: a by-value copy would live in local memory,
+    //  which TMA cannot read)
+    const CUtensorMap* pK = &tmK;
+    const CUtensorMap* pV = &tmV;
+    auto load_k = [=](int j, int stage, uint32_t ph) {
+      const int chunk = j / tiles_per_chunk;
+      const int key0 = (j - chunk * tiles_per_chunk) * V3_BK;
+      mbar_wait(&k_empty[stage], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[stage], L::KV_TILE_BYTES);
+        uint8_t* sk = smem + L::K_OFF + stage * L::KV_TILE_BYTES;
+        tma_load_5d(sk, pK, &k_full[stage], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sk + 8192, pK, &k_full[stage], 64, key0, head, batch, chunk, kEvictLast);
+      }
+      __syncwarp();
+    };
+    auto load_v = [=](int j, int stage, uint32_t ph) {
+      const int chunk = j / tiles_per_chunk;
+      const int key0 = (j - chunk * tiles_per_chunk) * V3_BK;
+      mbar_wait(&v_empty[stage], ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[stage], L::KV_TILE_BYTES);
+        uint8_t* sv = smem + L::V_OFF + stage * L::KV_TILE_BYTES;
+        tma_load_5d(sv, pV, &v_full[stage], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sv + 8192, pV, &v_full[stage], 64, key0, head, batch, chunk, kEvictLast);
+      }
+      __syncwarp();
+    };
+    for (int j = 0; j < 2 && j < n_kv; ++j) {
+      load_k(j, ks, kph);
+      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      load_v(j, vs, vph);
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+      if (j + 2 < n_kv) {
+        load_k(j + 2, ks, kph);
+        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer (warp converged; descriptors stay in uniform registers) =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V3_BK, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
+    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
+    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
+
+    auto issue_qk = [=](int i, int buf, int kstage) {
+      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::Q_TILE_BYTES);
+      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::KV_TILE_BYTES);
+      const uint32_t d = tmem_base + (2 * i + buf) * 64;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k)
+          mma_ss(d, qd + ((k >> 2) * (16384 / 16) + (k & 3) * 2), kd + ((k >> 2) * (8192 / 16) + (k & 3) * 2), idesc_qk, k != 0);
+        tc_commit(&s_full[2 * i + buf]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [=](int i, int buf, int vstage, bool first_tile) {
+      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::KV_TILE_BYTES, 8192);
+      const uint32_t d = tmem_base + 256 + i * 128;
+      const uint32_t pa = tmem_base + (2 * i + buf) * 64;  // P aliases S[i][buf]: 16 keys = 8 columns
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < V3_BK / 16; ++k)
+          mma_ts(d, pa + k * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);
+        tc_commit(&pv_done[i]);
+      }
+      __syncwarp();
+    };
+    auto commit = [=](uint64_t* bar) {
+      if (elect_one()) tc_commit(bar);
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    int ks = 0, vs = 0;       // stage of K tile (j+2) / V tile j
+    uint32_t kph = 0, vph = 0;
+    // prologue: S[.][0] from K0, S[.][1] from K1
+    for (int j = 0; j < 2 && j < n_kv; ++j) {
+      mbar_wait(&k_full[ks], kph);
+      tc_fence_after();
+      issue_qk(0, j, ks);
+      issue_qk(1, j, ks);
+      commit(&k_empty[ks]);
+      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      const uint32_t par = (j >> 1) & 1;
+      const bool has_next = (j + 2 < n_kv);
+      mbar_wait(&v_full[vs], vph);
+      if (has_next) mbar_wait(&k_full[ks], kph);
+      // ---- tile 0
+      mbar_wait(&p_ready[0 + buf], par);
+      tc_fence_after();
+      issue_pv(0, buf, vs, j == 0);
+      if (has_next) issue_qk(0, buf, ks);
+      if (j + 1 == n_kv) commit(&o_full[0]);
+      // ---- tile 1
+      mbar_wait(&p_ready[2 + buf], par);
+      tc_fence_after();
+      issue_pv(1, buf, vs, j == 0);
+      commit(&v_empty[vs]);
+      if (has_next) {
+        issue_qk(1, buf, ks);
+        commit(&k_empty[ks]);
+        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+      }
+      if (j + 1 == n_kv) commit(&o_full[1]);
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int wg = warp >> 2;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + wg * ATT_BQ + row_in_tile;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t o_addr = tmem_base + 256 + wg * 128 + lane_sel;
+
+    float m_used = -INFINITY;
+    float row_sum = 0.f;
+    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V3_BK;
+
+    for (int j = 0; j < n_kv; ++j) {
+      const int buf = j & 1;
+      const uint32_t s_addr = tmem_base + (2 * wg + buf) * 64 + lane_sel;
+      mbar_wait(&s_full[2 * wg + buf], (j >> 1) & 1);
+      tc_fence_after();
+      float sc[V3_BK];
+      tmem_ld_x32f(s_addr, sc);
+      tmem_ld_x32f(s_addr + 32, sc + 32);
+      tmem_wait_ld();
+      const int jj = j % tiles_per_chunk;
+      if (jj == tiles_per_chunk - 1 && last_valid < V3_BK) {
+#pragma unroll
+        for (int t = 0; t < V3_BK; ++t)
+          if (t >= last_valid) sc[t] = -INFINITY;
+      }
+      float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
+#pragma unroll
+      for (int t = 4; t < V3_BK; t += 4) {
+        mx0 = fmaxf(mx0, fmaxf(sc[t], sc[t + 1]));
+        mx1 = fmaxf(mx1, fmaxf(sc[t + 2], sc[t + 3]));
+      }
+      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
+      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        // rare: rescale O.  P·V of tile j-1 must have landed first (QK^T of tile j was issued before it).
+        mbar_wait(&pv_done[wg], (j - 1) & 1);
+        tc_fence_after();
+        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
+        if (need) {
+          m_used = m_new;
+          row_sum *= alpha;
+        }
+#pragma unroll 1
+        for (int c = 0; c < D; c += 32) {
+          float ov[32];
+          tmem_ld_x32f(o_addr + c, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
+          tmem_st_x32f(o_addr + c, ov);
+        }
+        tmem_wait_st();
+      }
+      const float mb = m_used * p.scale_log2;
+      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
+      uint64_t psum2 = pk2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float x0, x1, e0, e1;
+          upk2(fma2(pk2(sc[c * 32 + t], sc[c * 32 + t + 1]), scale2, nmb2), x0, x1);
+          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+            exp2_poly2(x0, x1, e0, e1);
+          } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+          }
+          psum2 = add2(psum2, pk2(e0, e1));
+          pk[t >> 1] = pack_bf16(e0, e1);
+        }
+        tmem_st_x16(s_addr + c * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_ready[2 * wg + buf]);
+      {
+        float s0, s1;
+        upk2(psum2, s0, s1);
+        row_sum += s0 + s1;
+      }
+    }
+
+    mbar_wait(&o_full[wg], 0);
+    tc_fence_after();
+    const float inv = 1.0f / row_sum;
+    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + (long long)q_row * p.o_stride_s;
+#pragma unroll 1
+    for (int c = 0; c < D; c += 32) {
+      float ov[32];
+      tmem_ld_x32f(o_addr + c, ov);
+      tmem_wait_ld();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
+          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
+          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
+          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c + t) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, int STAGES, int VER>  // VER: 1 = v1 (any head_dim), 2 = v2, 3 = v3 (head_dim 128)
 static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   using L = AttnSmem<D, STAGES>;
   using L2 = AttnV2Smem<2, 2>;
+  using L3 = AttnV3Smem<4, 4>;
+  constexpr bool V2 = (VER == 2);
   constexpr int BKV = V2 ? V2_BK : ATT_BK;
   CUtensorMap tmQ, tmK, tmV;
   const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
@@ -641,12 +998,33 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
   static bool attr_set = false;
   if constexpr (V2) {
-    auto kern = flash_attn_fwd_v2_kernel<2, 2>;
+    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
+    auto kern = emu == 0 ? flash_attn_fwd_v2_kernel<2, 2, 0>
+              : emu == 2 ? flash_attn_fwd_v2_kernel<2, 2, 2>
+              : emu == 3 ? flash_attn_fwd_v2_kernel<2, 2, 3>
+                         : flash_attn_fwd_v2_kernel<2, 2, 4>;
     if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
       attr_set = true;
     }
     kern<<<grid, V2_THREADS, L2::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  } else if constexpr (VER == 3) {
+    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
+    auto kern = emu == 0 ? flash_attn_fwd_v3_kernel<4, 4, 0>
+              : emu == 2 ? flash_attn_fwd_v3_kernel<4, 4, 2>
+              : emu == 3 ? flash_attn_fwd_v3_kernel<4, 4, 3>
+                         : flash_attn_fwd_v3_kernel<4, 4, 4>;
+    if (!attr_set) {
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
+      attr_set = true;
+    }
+    kern<<<grid, V3_THREADS, L3::TOTAL, stream>>>(tmQ, tmK, tmV, p);
   } else {
     auto kern = flash_attn_fwd_kernel<D, STAGES>;
     if (!attr_set) {
@@ -676,7 +1054,11 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
                 "flash_attn: kv_chunks * sk_chunk must equal sk");
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
-  static const int force_v1 = []() { const char* e = getenv("AMB_ATTN_V1"); return (e && e[0] == '1') ? 1 : 0; }();
-  if (a->head_dim == 128) return force_v1 ? launch_attn<128, 3, false>(a, s) : launch_attn<128, 3, true>(a, s);
-  return launch_attn<64, 4, false>(a, s);
+  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 3; }();
+  if (a->head_dim == 128) {
+    if (ver == 1) return launch_attn<128, 3, 1>(a, s);
+    if (ver == 2) return launch_attn<128, 3, 2>(a, s);
+    return launch_attn<128, 3, 3>(a, s);
+  }
+  return launch_attn<64, 4, 1>(a, s);
 }

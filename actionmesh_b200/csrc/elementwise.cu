@@ -18,44 +18,51 @@ struct CfgEulerParams {
   float dt;
   int n_branches;
   int n_frames;
-  long long n_per_frame;  // multiple of 4
+  long long n_per_frame;  // multiple of 8
   long long branch_stride, frame_stride, frame_offset;
 };
 
-// One thread = 4 consecutive latent elements: 16 B fp32 read + 8 B per bf16 branch read + 16 B write, all coalesced.
+// One thread = 8 consecutive latent elements: two 16 B fp32 reads + one 16 B read per bf16 branch + two 16 B writes, all
+// coalesced; every load of an element group is issued before the first use (4 independent 16 B requests in flight).
 __global__ void __launch_bounds__(256) cfg_euler_kernel(const CfgEulerParams p) {
-  const long long vec_per_frame = p.n_per_frame >> 2;
+  const long long vec_per_frame = p.n_per_frame >> 3;
   const long long total = vec_per_frame * p.n_frames;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int f = (int)(i / vec_per_frame);
     if (!p.frame_update[f]) continue;  // observed frame: bit-identical pass-through (scheduler.py:244-246)
-    const long long e = (i - (long long)f * vec_per_frame) << 2;
+    const long long e = (i - (long long)f * vec_per_frame) << 3;
     float4* xp = reinterpret_cast<float4*>(p.latents + (long long)f * p.n_per_frame + e);
     const __nv_bfloat16* pp = p.pred + (long long)f * p.frame_stride + p.frame_offset + e;
-    float4 x = *xp;
-    uint2 raw = __ldg(reinterpret_cast<const uint2*>(pp));
-    float2 a01 = unpack_bf16(raw.x), a23 = unpack_bf16(raw.y);
-    float v0 = a01.x, v1 = a01.y, v2 = a23.x, v3 = a23.y;
-    float q0 = v0, q1 = v1, q2 = v2, q3 = v3;  // previous branch
+    uint4 raw[kMaxBranches];
+#pragma unroll
+    for (int k = 0; k < kMaxBranches; ++k)
+      if (k < p.n_branches) raw[k] = __ldg(reinterpret_cast<const uint4*>(pp + (long long)k * p.branch_stride));
+    float4 x0 = xp[0], x1 = xp[1];
+    float v[8], q[8];
+    {
+      float2 a = unpack_bf16(raw[0].x), b = unpack_bf16(raw[0].y), c = unpack_bf16(raw[0].z), d = unpack_bf16(raw[0].w);
+      v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) q[t] = v[t];
+    }
 #pragma unroll
     for (int k = 1; k < kMaxBranches; ++k) {
       if (k < p.n_branches) {
-        uint2 r = __ldg(reinterpret_cast<const uint2*>(pp + (long long)k * p.branch_stride));
-        float2 b01 = unpack_bf16(r.x), b23 = unpack_bf16(r.y);
+        float2 a = unpack_bf16(raw[k].x), b = unpack_bf16(raw[k].y), c = unpack_bf16(raw[k].z), d = unpack_bf16(raw[k].w);
+        const float w[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
         const float s = p.scales[k - 1];
-        v0 += s * (b01.x - q0);
-        v1 += s * (b01.y - q1);
-        v2 += s * (b23.x - q2);
-        v3 += s * (b23.y - q3);
-        q0 = b01.x; q1 = b01.y; q2 = b23.x; q3 = b23.y;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          v[t] += s * (w[t] - q[t]);
+          q[t] = w[t];
+        }
       }
     }
-    x.x += p.dt * v0;
-    x.y += p.dt * v1;
-    x.z += p.dt * v2;
-    x.w += p.dt * v3;
-    *xp = x;
+    x0.x += p.dt * v[0]; x0.y += p.dt * v[1]; x0.z += p.dt * v[2]; x0.w += p.dt * v[3];
+    x1.x += p.dt * v[4]; x1.y += p.dt * v[5]; x1.z += p.dt * v[6]; x1.w += p.dt * v[7];
+    xp[0] = x0;
+    xp[1] = x1;
   }
 }
 
@@ -223,10 +230,10 @@ int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, co
   AMB_CHECK_ARG(latents && pred_bf16 && frame_update, "cfg_euler_step: null pointer");
   AMB_CHECK_ARG(n_branches >= 1 && n_branches <= kMaxBranches, "cfg_euler_step: n_branches %d not in [1,%d]", n_branches, kMaxBranches);
   AMB_CHECK_ARG(n_branches == 1 || scales_host, "cfg_euler_step: scales required");
-  AMB_CHECK_ARG(n_per_frame % 4 == 0 && frame_stride % 4 == 0 && frame_offset % 4 == 0 && branch_stride % 4 == 0,
-                "cfg_euler_step: sizes/strides must be multiples of 4 elements");
-  AMB_CHECK_ARG((reinterpret_cast<uintptr_t>(latents) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred_bf16) & 7) == 0,
-                "cfg_euler_step: misaligned pointers");
+  AMB_CHECK_ARG(n_per_frame % 8 == 0 && frame_stride % 8 == 0 && frame_offset % 8 == 0 && branch_stride % 8 == 0,
+                "cfg_euler_step: sizes/strides must be multiples of 8 elements");
+  AMB_CHECK_ARG((reinterpret_cast<uintptr_t>(latents) & 15) == 0 && (reinterpret_cast<uintptr_t>(pred_bf16) & 15) == 0,
+                "cfg_euler_step: pointers must be 16-byte aligned");
   if (n_frames <= 0 || n_per_frame <= 0) return AMB_OK;
   CfgEulerParams p;
   p.latents = latents;
@@ -240,7 +247,7 @@ int amb_cfg_euler_step(float* latents, const void* pred_bf16, int n_branches, co
   p.branch_stride = branch_stride;
   p.frame_stride = frame_stride;
   p.frame_offset = frame_offset;
-  const long long vecs = (n_per_frame >> 2) * (long long)n_frames;
+  const long long vecs = (n_per_frame >> 3) * (long long)n_frames;
   cfg_euler_kernel<<<grid_for(vecs, 256), 256, 0, (cudaStream_t)stream>>>(p);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;

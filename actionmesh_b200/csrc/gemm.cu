@@ -124,7 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform: role code stays on the uniform datapath
   const int lane = threadIdx.x & 31;
   constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 
@@ -160,53 +160,55 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_kb = p.K / BK;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ===================== TMA producer =====================
-      int s = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_tiles) * BM;
-        const int n0 = (tile % num_n_tiles) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[s], phase ^ 1);
+    // ===================== TMA producer (whole warp converged; one elected lane issues) =====================
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n_tiles) * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (kb < p.k_split_blocks) tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0, kEvictNormal);
           else tma_load_2d(sa, &tmA2, &full_bar[s], (kb - p.k_split_blocks) * BK, m0, kEvictNormal);
           tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0, kEvictLast);
-          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-      int s = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (whole warp converged; descriptors live in uniform registers) =====================
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    int s = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[s], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[s], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + L::A_BYTES;
+        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+        const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+        const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + L::A_BYTES);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            mma_ss(d_tmem, make_desc_kmajor_sw128(a_addr + k * 32), make_desc_kmajor_sw128(b_addr + k * 32), idesc,
-                   (kb | k) != 0);
-          }
+          for (int k = 0; k < BK / 16; ++k)  // +32 B per UMMA_K step == +2 in the descriptor's (addr >> 4) field
+            mma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs have read it
-          if (++s == STAGES) { s = 0; phase ^= 1; }
         }
-        tc_commit(&tmem_full[acc]);  // accumulator complete
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
       }
+      if (elect_one()) tc_commit(&tmem_full[acc]);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

@@ -278,6 +278,45 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 issue one instruction for two fp32 lanes)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for x <= ~0 on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic for 2^f
+// (max rel. error 6e-4, below bf16 rounding of P), exponent patched in by an integer add.  x is clamped at -126.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float& e1) {
+  const float kMagic = 12582912.0f;  // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t x = pk2(x0, x1);
+  const uint64_t t = add2(x, pk2(kMagic, kMagic));
+  const uint64_t n = add2(t, pk2(-kMagic, -kMagic));
+  const uint64_t f = fma2(n, pk2(-1.0f, -1.0f), x);
+  uint64_t p = fma2(f, pk2(0.0555041087f, 0.0555041087f), pk2(0.2402265070f, 0.2402265070f));
+  p = fma2(p, f, pk2(0.6931471806f, 0.6931471806f));
+  p = fma2(p, f, pk2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  upk2(p, p0, p1);
+  upk2(t, t0, t1);
+  e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+  e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 template <int N>
 __device__ __forceinline__ void reg_alloc() {  // whole warpgroup (4 warps) must execute
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
