@@ -11,11 +11,20 @@
 // TMEM: S0 [0,64) S1 [64,128) O0 [128,128+D) O1 [128+D,128+2D)  -> 512 columns allocated.
 // The issue order  S0 S1 | PV0 S0' PV1 S1' | ...  keeps the tensor pipe busy with tile 1 while warpgroup 0 is in softmax.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/actionmesh_b200.h"
 
 namespace amb {
+
+// debug: timeline buffer set through amb_debug_set_attn_trace (never on the product path unless set)
+static long long* g_attn_trace = nullptr;
+constexpr int TRACE_J0 = 100, TRACE_NJ = 16, TRACE_EV = 8;  // iterations [100,116), 8 event slots per (role, iteration)
+__device__ __forceinline__ void trace_ev(long long* tr, int role, int j, int ev) {
+  if (tr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= TRACE_J0 && j < TRACE_J0 + TRACE_NJ)
+    tr[(role * TRACE_NJ + (j - TRACE_J0)) * TRACE_EV + ev] = clock64();
+}
 
 constexpr int ATT_BQ = 128;   // rows per query tile
 constexpr int ATT_BK = 64;    // keys per K/V tile
@@ -27,6 +36,7 @@ struct AttnParams {
   int heads, sq, sk;
   int kv_chunks, sk_chunk;   // kv split into chunks along the outermost tensor-map coordinate
   float scale_log2;          // scale * log2(e)
+  long long* trace;          // optional device buffer for the clock64 timeline of CTA (0,0,0) (debug; NULL = off)
 };
 
 template <int D, int STAGES>
@@ -332,7 +342,10 @@ struct AttnV2Smem {
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
-template <int KSTAGES, int VSTAGES, int EMU>  // EMU: every EMU-th pair of exponentials runs on the FMA pipes (0 = none)
+// EMU: every EMU-th pair of exponentials runs on the FMA pipes (0 = none).  SEQ: the two softmax warpgroups take turns
+// in the MUFU-bound exponential section (named barriers), which staggers them so that one warpgroup's softmax overlaps
+// the other tile's MMAs instead of both contending for the MUFU and then both waiting on the tensor pipe.
+template <int KSTAGES, int VSTAGES, int EMU, bool SEQ>
 __global__ void __launch_bounds__(V2_THREADS, 1)
 flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -523,11 +536,19 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     float row_sum = 0.f;
     const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V2_BK;
 
-    for (int j = 0; j < n_kv; ++j) {
+    // One key-tile step.  MASKED is a compile-time flag: only the last (partial) tile of a chunk carries the tail
+    // masking code, so the hot path has no per-element select.
+    auto softmax_step = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       mbar_wait(&s_full[wg], j & 1);
       tc_fence_after();
-      const int jj = j % tiles_per_chunk;
-      const int valid = (jj == tiles_per_chunk - 1) ? last_valid : V2_BK;
+      if (EMU == 8) {  // timing experiment only (AMB_ATTN_EMU=8): tensor pipe + barriers alone, no softmax work
+        tc_fence_before();
+        mbar_arrive(&p_a[wg]);
+        mbar_arrive(&p_b[wg]);
+        row_sum = 1.f;
+        return;
+      }
       // ---- one TMEM read of the 128 scores of this row (4 back-to-back loads, one wait)
       float sc[V2_BK];
       tmem_ld_x32f(s_addr, sc);
@@ -535,10 +556,10 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       tmem_ld_x32f(s_addr + 64, sc + 64);
       tmem_ld_x32f(s_addr + 96, sc + 96);
       tmem_wait_ld();
-      if (valid < V2_BK) {
+      if (MASKED) {
 #pragma unroll
         for (int t = 0; t < V2_BK; ++t)
-          if (t >= valid) sc[t] = -INFINITY;
+          if (t >= last_valid) sc[t] = -INFINITY;
       }
       float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
 #pragma unroll
@@ -569,6 +590,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tmem_wait_st();
       }
       // ---- exponentials; bf16 P written over the consumed S columns, handed to the MMA warp in two halves
+      if (SEQ && (wg == 1 || j > 0)) named_bar_sync(1 + wg, 256);  // my turn on the MUFU (warpgroup 0 goes first)
       const float mb = m_used * p.scale_log2;
       const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
       uint64_t psum2 = pk2(0.f, 0.f);
@@ -579,7 +601,10 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int t = 0; t < 32; t += 2) {
           float x0, x1, e0, e1;
           upk2(fma2(pk2(sc[c * 32 + t], sc[c * 32 + t + 1]), scale2, nmb2), x0, x1);
-          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+          if (EMU == 9) {  // timing experiment only (AMB_ATTN_EMU=9): no exponentials, wrong numerics
+            e0 = x0;
+            e1 = x1;
+          } else if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
             exp2_poly2(x0, x1, e0, e1);
           } else {
             e0 = ex2_approx(x0);  // exp2(-inf) = 0 masks the tail
@@ -595,6 +620,7 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
           mbar_arrive(&p_a[wg]);
         }
       }
+      if (SEQ && !(wg == 1 && j + 1 == n_kv)) named_bar_arrive(2 - wg, 256);  // hand the MUFU to the other warpgroup
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_b[wg]);
@@ -603,6 +629,15 @@ flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         upk2(psum2, s0, s1);
         row_sum += s0 + s1;
       }
+    };
+
+    const bool has_tail = last_valid < V2_BK;
+    int jj = 0;  // tile index inside the current K/V chunk (kept incrementally: no integer division in the loop)
+    for (int j = 0; j < n_kv; ++j) {
+      const bool tail = has_tail && (jj == tiles_per_chunk - 1);
+      if (++jj == tiles_per_chunk) jj = 0;
+      if (tail) softmax_step(j, std::true_type{});
+      else softmax_step(j, std::false_type{});
     }
 
     mbar_wait(&o_full[wg], 0);
@@ -956,13 +991,385 @@ flash_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
 }
 
+
+// =====================================================================================================================
+// v4 (head_dim 128): v2's data flow (128-key tiles, P in TMEM, TS-form P·V, P handed over in two halves) with TWO threads
+// per query row.  16 softmax warps: for query tile i, warps 8i..8i+3 own keys 0-63 of every 128-key tile and warps
+// 8i+4..8i+7 own keys 64-127 (a warp may only touch TMEM lanes 32*(warp%4)+[0,32), so both halves cover all 4 lane
+// quarters).  Halving the per-thread work halves the softmax latency on the critical QK -> softmax -> PV chain and gives
+// every SM sub-partition 4 softmax warps to interleave.  The two halves of a row exchange their partial row maxima
+// through shared memory (one 256-thread named barrier per tile step); partial row sums are combined once at the end.
+//   warp 16 = TMA producer, warp 17 = MMA issuer + TMEM owner.       TMEM as in v2.
+// =====================================================================================================================
+constexpr int V4_THREADS = 576;
+
+template <int KSTAGES, int VSTAGES>
+struct AttnV4Smem {
+  static constexpr int TILE_BYTES = 128 * 128 * 2;
+  static constexpr int Q_OFF = 0;
+  static constexpr int K_OFF = 2 * TILE_BYTES;
+  static constexpr int V_OFF = K_OFF + KSTAGES * TILE_BYTES;
+  static constexpr int XCH_OFF = V_OFF + VSTAGES * TILE_BYTES;          // float[2 tiles][2 halves][128 rows]
+  static constexpr int BAR_OFF = XCH_OFF + 2 * 2 * 128 * 4;
+  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 2 + 2 + 2 + 2;
+  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+template <int KSTAGES, int VSTAGES, int EMU>
+__global__ void __launch_bounds__(V4_THREADS, 1)  // 18 warps are allocated as 5 warpgroups: 96 registers per thread
+flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnV4Smem<KSTAGES, VSTAGES>;
+  constexpr int D = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + KSTAGES;
+  uint64_t* v_full = k_empty + KSTAGES;
+  uint64_t* v_empty = v_full + VSTAGES;
+  uint64_t* s_full = v_empty + VSTAGES;  // [2]
+  uint64_t* p_a = s_full + 2;            // [2] keys 0-63 of P ready (arrivals: the 128 "half 0" threads)
+  uint64_t* p_b = p_a + 2;               // [2] keys 64-127 of P ready (the 128 "half 1" threads)
+  uint64_t* o_full = p_b + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * ATT_BQ);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int tiles_per_chunk = (p.sk_chunk + V2_BK - 1) / V2_BK;
+  const int n_kv = p.kv_chunks * tiles_per_chunk;
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 17) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_a[i], 128);
+        mbar_init(&p_b[i], 128);
+        mbar_init(&o_full[i], 1);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 16) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * L::TILE_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int c = 0; c < 2; ++c)
+          tma_load_4d(smem + L::Q_OFF + i * L::TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
+                      batch, kEvictFirst);
+    }
+    __syncwarp();
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const int chunk = j / tiles_per_chunk;
+      const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
+      mbar_wait(&k_empty[ks], kph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[ks], L::TILE_BYTES);
+        uint8_t* sk = smem + L::K_OFF + ks * L::TILE_BYTES;
+        tma_load_5d(sk, &tmK, &k_full[ks], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, batch, chunk, kEvictLast);
+      }
+      __syncwarp();
+      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
+      mbar_wait(&v_empty[vs], vph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[vs], L::TILE_BYTES);
+        uint8_t* sv = smem + L::V_OFF + vs * L::TILE_BYTES;
+        tma_load_5d(sv, &tmV, &v_full[vs], 0, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, batch, chunk, kEvictLast);
+      }
+      __syncwarp();
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+    }
+  } else if (warp == 17) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V2_BK, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
+    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
+    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
+    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
+
+    auto issue_qk = [=](int i, int kstage) {
+      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::TILE_BYTES);
+      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::TILE_BYTES);
+      const uint32_t d = tmem_base + i * 128;
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < D / 16; ++k) {
+          const uint32_t off = (k >> 2) * (16384 / 16) + (k & 3) * 2;
+          mma_ss(d, qd + off, kd + off, idesc_qk, k != 0);
+        }
+        tc_commit(&s_full[i]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv_half = [=](int i, int vstage, int half, bool first_tile) {
+      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::TILE_BYTES, 16384);
+      const uint32_t d = tmem_base + 256 + i * 128;
+      // P of key-half h lives in the first 32 columns of THAT half's own S columns (h*64): a half's P never overwrites
+      // scores the other half's threads still have to re-read.
+      const uint32_t pa = tmem_base + i * 128 + half * 64;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const int k = half * 4 + kk;
+          mma_ts(d, pa + kk * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);
+        }
+      }
+      __syncwarp();
+    };
+    auto commit = [=](uint64_t* bar) {
+      if (elect_one()) tc_commit(bar);
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    commit(&k_empty[0]);
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      int ks_next = ks + 1;
+      uint32_t kph_next = kph;
+      if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
+      const bool has_next = (j + 1 < n_kv);
+      const uint32_t par = j & 1;
+      mbar_wait(&v_full[vs], vph);
+      mbar_wait(&p_a[0], par);
+      if (lane == 0) trace_ev(p.trace, 4, j, 0);
+      tc_fence_after();
+      issue_pv_half(0, vs, 0, j == 0);
+      mbar_wait(&p_b[0], par);
+      if (lane == 0) trace_ev(p.trace, 4, j, 1);
+      tc_fence_after();
+      issue_pv_half(0, vs, 1, j == 0);
+      if (has_next) {
+        mbar_wait(&k_full[ks_next], kph_next);
+        tc_fence_after();
+        issue_qk(0, ks_next);
+      } else {
+        commit(&o_full[0]);
+      }
+      if (lane == 0) trace_ev(p.trace, 4, j, 2);
+      mbar_wait(&p_a[1], par);
+      if (lane == 0) trace_ev(p.trace, 4, j, 3);
+      tc_fence_after();
+      issue_pv_half(1, vs, 0, j == 0);
+      mbar_wait(&p_b[1], par);
+      if (lane == 0) trace_ev(p.trace, 4, j, 4);
+      tc_fence_after();
+      issue_pv_half(1, vs, 1, j == 0);
+      commit(&v_empty[vs]);
+      if (has_next) {
+        issue_qk(1, ks_next);
+        commit(&k_empty[ks_next]);
+      } else {
+        commit(&o_full[1]);
+      }
+      if (lane == 0) trace_ev(p.trace, 4, j, 5);
+      ks = ks_next;
+      kph = kph_next;
+      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
+    }
+  } else {
+    // ===================== softmax: 2 tiles x 2 key-halves x 4 lane quarters =====================
+    const int tile = warp >> 3;
+    const int half = (warp >> 2) & 1;
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    const int q_row = q0 + tile * ATT_BQ + row_in_tile;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_base + tile * 128 + half * 64 + lane_sel;   // my 64 score columns
+    const uint32_t p_addr = s_addr;                                          // my 32 packed-P columns alias my own scores
+    const uint32_t o_addr = tmem_base + 256 + tile * 128 + half * 64 + lane_sel;  // my 64 O columns (rescale / epilogue)
+    float* x_mine = xch + (tile * 2 + half) * 128 + row_in_tile;
+    const float* x_other = xch + (tile * 2 + (half ^ 1)) * 128 + row_in_tile;
+    uint64_t* my_p_bar = half ? &p_b[tile] : &p_a[tile];
+    const uint32_t bar_id = 1 + tile;  // named barrier of this tile's 256 softmax threads
+
+    float m_used = -INFINITY;
+    float row_sum = 0.f;  // partial: my 64 keys of every tile
+    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V2_BK;  // valid keys in the last tile of a chunk
+
+    auto softmax_step = [&](int j, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
+      const bool tracer = (quarter == 0 && lane == 0);
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 0);
+      mbar_wait(&s_full[tile], j & 1);
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 1);
+      tc_fence_after();
+      // ---- pass 1: partial row max over my 64 scores (two 32-column reads; the values are re-read in pass 2 to keep
+      //      the register footprint at 32 scores: 18 warps are allocated as 5 warpgroups => 96 registers per thread)
+      float mxp;
+      {
+        float a[32], b[32];
+        tmem_ld_x32f(s_addr, a);
+        tmem_ld_x32f(s_addr + 32, b);
+        tmem_wait_ld();
+        if (MASKED) {
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            if (half * 64 + t >= last_valid) a[t] = -INFINITY;
+            if (half * 64 + 32 + t >= last_valid) b[t] = -INFINITY;
+          }
+        }
+        float mx0 = fmaxf(a[0], a[1]), mx1 = fmaxf(b[0], b[1]);
+#pragma unroll
+        for (int t = 2; t < 32; t += 2) {
+          mx0 = fmaxf(mx0, fmaxf(a[t], a[t + 1]));
+          mx1 = fmaxf(mx1, fmaxf(b[t], b[t + 1]));
+        }
+        mxp = fmaxf(mx0, mx1);
+      }
+      // exchange the partial row max with the thread that owns the other 64 keys of this row
+      *x_mine = mxp;
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 2);
+      named_bar_sync(bar_id, 256);
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 3);
+      const float m_new = fmaxf(m_used, fmaxf(mxp, *x_other));
+      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
+      if (j == 0) {
+        m_used = m_new;
+      } else if (__any_sync(0xffffffffu, need)) {
+        // rare: rescale my 64 columns of O (both halves of a row take the same decision: same m values).  Both halves
+        // finish long before either hands over P (the exponentials follow), so P·V never meets a half-rescaled O.
+        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
+        if (need) {
+          m_used = m_new;
+          row_sum *= alpha;
+        }
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          float ov[32];
+          tmem_ld_x32f(o_addr + c, ov);
+          tmem_wait_ld();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
+          tmem_st_x32f(o_addr + c, ov);
+        }
+        tmem_wait_st();
+        named_bar_sync(3 + tile * 4 + quarter, 64);  // my row-partner warp has rescaled its O columns too
+      }
+      // ---- pass 2: exponentials, 32 scores at a time; bf16 P written over my own already-consumed S columns
+      const float mb = m_used * p.scale_log2;
+      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
+      uint64_t psum2 = pk2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float sc[32];
+        tmem_ld_x32f(s_addr + c * 32, sc);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float x0, x1, e0, e1;
+          upk2(fma2(pk2(sc[t], sc[t + 1]), scale2, nmb2), x0, x1);
+          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+            exp2_poly2(x0, x1, e0, e1);
+          } else {
+            e0 = ex2_approx(x0);
+            e1 = ex2_approx(x1);
+          }
+          if (MASKED) {  // the scores were re-read unmasked: zero the tail keys explicitly
+            if (half * 64 + c * 32 + t >= last_valid) e0 = 0.f;
+            if (half * 64 + c * 32 + t + 1 >= last_valid) e1 = 0.f;
+          }
+          psum2 = add2(psum2, pk2(e0, e1));
+          pk[t >> 1] = pack_bf16(e0, e1);
+        }
+        tmem_st_x16(p_addr + c * 16, pk);
+      }
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 4);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(my_p_bar);
+      if (tracer) trace_ev(p.trace, tile * 2 + half, j, 5);
+      {
+        float s0, s1;
+        upk2(psum2, s0, s1);
+        row_sum += s0 + s1;
+      }
+    };
+
+    const bool has_tail = last_valid < V2_BK;
+    int jj = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const bool tail = has_tail && (jj == tiles_per_chunk - 1);
+      if (++jj == tiles_per_chunk) jj = 0;
+      if (tail) softmax_step(j, std::true_type{});
+      else softmax_step(j, std::false_type{});
+    }
+
+    // ---- epilogue: combine the two partial row sums, normalise my 64 columns of O, store bf16
+    mbar_wait(&o_full[tile], 0);
+    tc_fence_after();
+    named_bar_sync(bar_id, 256);  // everyone is past the last max exchange before the buffer is reused for the sums
+    *x_mine = row_sum;
+    named_bar_sync(bar_id, 256);
+    const float inv = 1.0f / (row_sum + *x_other);
+    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h +
+                          (long long)q_row * p.o_stride_s + half * 64;
+#pragma unroll 1
+    for (int c = 0; c < 64; c += 32) {
+      float ov[32];
+      tmem_ld_x32f(o_addr + c, ov);
+      tmem_wait_ld();
+      if (q_row < p.sq) {
+#pragma unroll
+        for (int t = 0; t < 32; t += 8) {
+          uint4 pk;
+          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
+          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
+          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
+          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
+          *reinterpret_cast<uint4*>(orow + c + t) = pk;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int D, int STAGES, int VER>  // VER: 1 = v1 (any head_dim), 2 = v2, 3 = v3 (head_dim 128)
 static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   using L = AttnSmem<D, STAGES>;
   using L2 = AttnV2Smem<2, 2>;
   using L3 = AttnV3Smem<4, 4>;
+  using L4 = AttnV4Smem<2, 2>;
   constexpr bool V2 = (VER == 2);
-  constexpr int BKV = V2 ? V2_BK : ATT_BK;
+  constexpr int BKV = (VER == 2 || VER == 4) ? V2_BK : ATT_BK;
   CUtensorMap tmQ, tmK, tmV;
   const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
   const int sk_chunk = chunks > 1 ? a->sk_chunk : a->sk;
@@ -994,23 +1401,42 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   p.heads = a->heads; p.sq = a->sq; p.sk = a->sk;
   p.kv_chunks = chunks; p.sk_chunk = sk_chunk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
 
   dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
   static bool attr_set = false;
   if constexpr (V2) {
     static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
-    auto kern = emu == 0 ? flash_attn_fwd_v2_kernel<2, 2, 0>
-              : emu == 2 ? flash_attn_fwd_v2_kernel<2, 2, 2>
-              : emu == 3 ? flash_attn_fwd_v2_kernel<2, 2, 3>
-                         : flash_attn_fwd_v2_kernel<2, 2, 4>;
+    static const int seq = []() { const char* e = getenv("AMB_ATTN_SEQ"); return e ? atoi(e) : 0; }();
+    using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
+    static const KernT table[2][6] = {
+        {flash_attn_fwd_v2_kernel<2, 2, 0, false>, flash_attn_fwd_v2_kernel<2, 2, 2, false>,
+         flash_attn_fwd_v2_kernel<2, 2, 3, false>, flash_attn_fwd_v2_kernel<2, 2, 4, false>,
+         flash_attn_fwd_v2_kernel<2, 2, 9, false>, flash_attn_fwd_v2_kernel<2, 2, 8, false>},
+        {flash_attn_fwd_v2_kernel<2, 2, 0, true>, flash_attn_fwd_v2_kernel<2, 2, 2, true>,
+         flash_attn_fwd_v2_kernel<2, 2, 3, true>, flash_attn_fwd_v2_kernel<2, 2, 4, true>,
+         flash_attn_fwd_v2_kernel<2, 2, 9, true>, flash_attn_fwd_v2_kernel<2, 2, 8, true>}};
+    const int ei = emu == 0 ? 0 : emu == 2 ? 1 : emu == 3 ? 2 : emu == 9 ? 4 : emu == 8 ? 5 : 3;
+    KernT kern = table[seq ? 1 : 0][ei];
     if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v2_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
+      for (int a_ = 0; a_ < 2; ++a_)
+        for (int b_ = 0; b_ < 6; ++b_)
+          AMB_CHECK_CUDA(cudaFuncSetAttribute(table[a_][b_], cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
       attr_set = true;
     }
     kern<<<grid, V2_THREADS, L2::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  } else if constexpr (VER == 4) {
+    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
+    auto kern = emu == 0 ? flash_attn_fwd_v4_kernel<2, 2, 0>
+              : emu == 2 ? flash_attn_fwd_v4_kernel<2, 2, 2>
+                         : flash_attn_fwd_v4_kernel<2, 2, 4>;
+    if (!attr_set) {
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
+      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
+      attr_set = true;
+    }
+    kern<<<grid, V4_THREADS, L4::TOTAL, stream>>>(tmQ, tmK, tmV, p);
   } else if constexpr (VER == 3) {
     static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
     auto kern = emu == 0 ? flash_attn_fwd_v3_kernel<4, 4, 0>
@@ -1041,6 +1467,11 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
 
 using namespace amb;
 
+extern "C" int amb_debug_set_attn_trace(void* device_buffer) {
+  amb::g_attn_trace = reinterpret_cast<long long*>(device_buffer);
+  return AMB_OK;
+}
+
 extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
   AMB_CHECK_ARG(a && a->q && a->k && a->v && a->o, "flash_attn: null pointer");
   AMB_CHECK_ARG(a->batch > 0 && a->heads > 0 && a->sq > 0 && a->sk > 0, "flash_attn: bad shape b=%d h=%d sq=%d sk=%d",
@@ -1054,11 +1485,12 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
                 "flash_attn: kv_chunks * sk_chunk must equal sk");
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
-  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 3; }();
+  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 4; }();  // v4 is the product kernel; 1-3 kept for A/B
   if (a->head_dim == 128) {
     if (ver == 1) return launch_attn<128, 3, 1>(a, s);
     if (ver == 2) return launch_attn<128, 3, 2>(a, s);
-    return launch_attn<128, 3, 3>(a, s);
+    if (ver == 3) return launch_attn<128, 3, 3>(a, s);
+    return launch_attn<128, 3, 4>(a, s);
   }
   return launch_attn<64, 4, 1>(a, s);
 }

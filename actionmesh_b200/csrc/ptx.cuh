@@ -277,6 +277,9 @@ __device__ __forceinline__ void tmem_st_x32f(uint32_t taddr, const float* v) {
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 issue one instruction for two fp32 lanes)
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {

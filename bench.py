@@ -251,6 +251,38 @@ def run_b200(args):
     e2e_val = world * e2e_steps / (float(e2e_ms.item()) / 1e3)
     h2d_bytes = (host_lat.numel() + host_ctx.numel() + host_mask.numel()) * 4
 
+    # ---------------- N > 1: also time ONE window frame-sharded over all ranks (strong scaling, K/V all-gather)
+    temporal = None
+    if world > 1 and 16 % world == 0:
+        from actionmesh_b200.window_shard import FrameShard
+
+        shard = FrameShard()
+        g0 = torch.Generator(device="cpu").manual_seed(44)
+        lat_t = torch.randn(1, T, N, C, generator=g0).to(dev)      # identical window on every rank
+        ctx_t = torch.randn(1, T, S, Dc, generator=torch.Generator().manual_seed(5)).to(dev)
+        sch3 = B200SchedulerFlow(num_inference_steps=W + K, shift=3.0, is_additive=True)
+        ev3 = {}
+
+        def cb3(step, total):
+            if step == W:
+                ev3["t0"] = torch.cuda.Event(enable_timing=True)
+                ev3["t0"].record()
+            if step == total:
+                ev3["t1"] = torch.cuda.Event(enable_timing=True)
+                ev3["t1"].record()
+
+        barrier()
+        if W == 0:
+            cb3(0, W + K)
+        sch3.denoise(model, cf, lat_t, ctx_t, device=dev, mask=mask, framestep=framestep, step_callback=cb3, shard=shard)
+        barrier()
+        t3 = torch.tensor([ev3["t0"].elapsed_time(ev3["t1"])], device=dev, dtype=torch.float64)
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        temporal = {"value": K / (float(t3.item()) / 1e3), "unit": UNIT, "ms_per_step": float(t3.item()) / K,
+                    "scaling": "strong", "frames_per_rank": T // world,
+                    "note": "ONE default window, frames sharded over the ranks, temporal-attention K/V all-gathered per "
+                            "layer over NCCL (window_shard.py); steps/s of that single window"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -292,6 +324,8 @@ def run_b200(args):
                         "window inputs are copied once (amortised per step), the latents are read back every step"},
         "gpu_launches": launches, "clocks": clocks,
     }
+    if temporal is not None:
+        line["temporal_shard"] = temporal
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

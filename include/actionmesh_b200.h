@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 5
+#define AMB_ABI_VERSION 6
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -136,6 +136,10 @@ typedef struct amb_attn_args {
 } amb_attn_args;
 
 int amb_flash_attn_fwd(const amb_attn_args* args, amb_stream_t stream);
+
+/* Debug only: device buffer (5 roles x 16 iterations x 8 events of int64 clock64 stamps) receiving the role timeline of
+ * CTA (0,0,0) of the head_dim-128 attention kernel; NULL switches tracing off (the default). */
+int amb_debug_set_attn_trace(void* device_buffer);
 
 #ifdef __cplusplus
 }

@@ -105,6 +105,29 @@ def test_flash_attention(probe, name, args, kw):
     assert not res[name]["nan"] and res[name]["rel_fro"] < BF16_REL, res[name]
 
 
+def test_flash_attention_late_rescale(probe):
+    """Running-max rescale AFTER the first key tile: keys are ordered so that every row's maximum keeps growing by more
+    than the lazy-rescale threshold (2^8) along the key axis, with a ragged tail tile."""
+    from actionmesh_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    B, S, H, D = 1, 128 * 9 + 17, 2, 128
+    q = torch.randn(B, S, H, D, generator=g)
+    k = torch.randn(B, S, H, D, generator=g) * 0.05
+    v = torch.randn(B, S, H, D, generator=g)
+    # key t gets a component along the mean query direction growing with t => logits ramp up by ~12 nats per tile
+    qdir = q.mean(dim=1, keepdim=True)
+    qdir = qdir / qdir.norm(dim=-1, keepdim=True)
+    ramp = (torch.arange(S, dtype=torch.float32) / 128.0).floor()[None, :, None, None]
+    k = k + ramp * 12.0 * qdir * (math.sqrt(D) / (q * qdir).sum(-1, keepdim=True).abs().mean())
+    q, k, v = (t.cuda().bfloat16() for t in (q, k, v))
+    o = torch.empty_like(q)
+    ops.flash_attn(q, k, v, o, 1 / math.sqrt(D))
+    ref = probe._attn_ref(q, k, v, 1 / math.sqrt(D))
+    err = float((o.float() - ref).norm() / ref.norm())
+    assert err < BF16_REL and not torch.isnan(o).any(), err
+
+
 def test_flash_attention_full_window_properties(probe):
     """Default-config shape (B=2, H=16, S=32 784): with V == 1 every output must be exactly 1 (softmax rows sum to 1),
     and permuting the keys must not change the result beyond accumulation-order noise."""
