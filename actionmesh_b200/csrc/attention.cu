@@ -1276,18 +1276,21 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         tmem_wait_st();
         named_bar_sync(3 + tile * 4 + quarter, 64);  // my row-partner warp has rescaled its O columns too
       }
-      // ---- pass 2: exponentials, 32 scores at a time; bf16 P written over my own already-consumed S columns
+      // ---- pass 2: exponentials in four 16-score chunks; the TMEM read of chunk c+1 is issued before the math of chunk c
+      //      (software prefetch: its latency hides behind 16 exponentials); bf16 P overwrites my own consumed S columns
       const float mb = m_used * p.scale_log2;
       const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
       uint64_t psum2 = pk2(0.f, 0.f);
+      float scb[2][16];
+      tmem_ld_x16f(s_addr, scb[0]);
+      tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float sc[32];
-        tmem_ld_x32f(s_addr + c * 32, sc);
-        tmem_wait_ld();
-        uint32_t pk[16];
+      for (int c = 0; c < 4; ++c) {
+        if (c < 3) tmem_ld_x16f(s_addr + (c + 1) * 16, scb[(c + 1) & 1]);
+        const float* sc = scb[c & 1];
+        uint32_t pk[8];
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
+        for (int t = 0; t < 16; t += 2) {
           float x0, x1, e0, e1;
           upk2(fma2(pk2(sc[t], sc[t + 1]), scale2, nmb2), x0, x1);
           if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
@@ -1297,13 +1300,14 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             e1 = ex2_approx(x1);
           }
           if (MASKED) {  // the scores were re-read unmasked: zero the tail keys explicitly
-            if (half * 64 + c * 32 + t >= last_valid) e0 = 0.f;
-            if (half * 64 + c * 32 + t + 1 >= last_valid) e1 = 0.f;
+            if (half * 64 + c * 16 + t >= last_valid) e0 = 0.f;
+            if (half * 64 + c * 16 + t + 1 >= last_valid) e1 = 0.f;
           }
           psum2 = add2(psum2, pk2(e0, e1));
           pk[t >> 1] = pack_bf16(e0, e1);
         }
-        tmem_st_x16(p_addr + c * 16, pk);
+        tmem_wait_ld();                       // chunk c+1 has landed (and chunk c's columns are fully consumed)
+        tmem_st_x8(p_addr + c * 8, pk);       // P of chunk c -> columns [8c, 8c+8): always inside already-read scores
       }
       if (tracer) trace_ev(p.trace, tile * 2 + half, j, 4);
       tmem_wait_st();

@@ -126,6 +126,33 @@ class B200ImageEncoder:
         self._w = w
         self._loaded = True
 
+    def init_random_(self, seed: int = 1235) -> None:
+        """Synthetic DinoV2 weights with the HF key names (benchmarks only; no checkpoints offline)."""
+        dev = self._device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        D, P, F_ = self.hidden_size, self.patch_size, self.hidden_size * self.mlp_ratio
+
+        def rnd(*shape, scale=0.02):
+            return torch.randn(*shape, generator=g, device=dev) * scale
+
+        sd = {"embeddings.cls_token": rnd(1, 1, D, scale=0.2),
+              "embeddings.position_embeddings": rnd(1, 1 + 37 * 37, D, scale=0.2),
+              "embeddings.patch_embeddings.projection.weight": rnd(D, 3, P, P),
+              "embeddings.patch_embeddings.projection.bias": rnd(D),
+              "layernorm.weight": torch.ones(D, device=dev), "layernorm.bias": torch.zeros(D, device=dev)}
+        for i in range(self.num_layers):
+            p_ = f"encoder.layer.{i}."
+            for n in ("norm1", "norm2"):
+                sd[p_ + n + ".weight"], sd[p_ + n + ".bias"] = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+            for n in ("query", "key", "value"):
+                sd[p_ + f"attention.attention.{n}.weight"], sd[p_ + f"attention.attention.{n}.bias"] = rnd(D, D), rnd(D)
+            sd[p_ + "attention.output.dense.weight"], sd[p_ + "attention.output.dense.bias"] = rnd(D, D), rnd(D)
+            sd[p_ + "layer_scale1.lambda1"] = torch.full((D,), 0.5, device=dev)
+            sd[p_ + "layer_scale2.lambda1"] = torch.full((D,), 0.5, device=dev)
+            sd[p_ + "mlp.fc1.weight"], sd[p_ + "mlp.fc1.bias"] = rnd(F_, D), rnd(F_)
+            sd[p_ + "mlp.fc2.weight"], sd[p_ + "mlp.fc2.bias"] = rnd(D, F_), rnd(D)
+        self.load_state_dict(sd)
+
     # ---- encode
     @torch.no_grad()
     def encode_images(self, images: List) -> torch.Tensor:
