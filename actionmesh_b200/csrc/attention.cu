@@ -1280,7 +1280,7 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       //      (software prefetch: its latency hides behind 16 exponentials); bf16 P overwrites my own consumed S columns
       const float mb = m_used * p.scale_log2;
       const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
-      uint64_t psum2 = pk2(0.f, 0.f);
+      uint64_t psum2 = pk2(0.f, 0.f), psum2b = pk2(0.f, 0.f);  // two independent accumulation chains
       float scb[2][16];
       tmem_ld_x16f(s_addr, scb[0]);
       tmem_wait_ld();
@@ -1303,7 +1303,8 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             if (half * 64 + c * 16 + t >= last_valid) e0 = 0.f;
             if (half * 64 + c * 16 + t + 1 >= last_valid) e1 = 0.f;
           }
-          psum2 = add2(psum2, pk2(e0, e1));
+          if ((t >> 1) & 1) psum2b = add2(psum2b, pk2(e0, e1));
+          else psum2 = add2(psum2, pk2(e0, e1));
           pk[t >> 1] = pack_bf16(e0, e1);
         }
         tmem_wait_ld();                       // chunk c+1 has landed (and chunk c's columns are fully consumed)
@@ -1316,7 +1317,7 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       if (tracer) trace_ev(p.trace, tile * 2 + half, j, 5);
       {
         float s0, s1;
-        upk2(psum2, s0, s1);
+        upk2(add2(psum2, psum2b), s0, s1);
         row_sum += s0 + s1;
       }
     };
