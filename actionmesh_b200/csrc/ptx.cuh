@@ -262,6 +262,16 @@ __device__ __forceinline__ void tmem_ld_x32f(uint32_t taddr, float* v) {
         "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld_x8f(uint32_t taddr, float* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x16f(uint32_t taddr, float* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
