@@ -7,6 +7,7 @@
 //                               per-head RMSNorm + RoPE; 16-byte global stores)
 // Two TMEM accumulator buffers (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1.
 // Tiles are visited n-fastest so the CTAs of one wave share A rows through L2 and W stays L2-resident.
+#include <cstdlib>
 #include "common.cuh"
 #include "ptx.cuh"
 #include "../../include/actionmesh_b200.h"
@@ -108,6 +109,72 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
       for (int t = 0; t < 8; ++t) v[j + t] += r[t];
     }
     store8(p.C, p.c_fp32, drow * p.ldc + col + j, v + j);
+  }
+}
+
+// Epilogue of one 128 x BN accumulator tile held in TMEM (thread == row): bias / GELU / LayerScale / residual, or the
+// per-head RMSNorm (+RoPE) path, then 16-byte global stores.  Shared by the 1-CTA and the 2-CTA kernels.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int n0, int row, long long drow,
+                                              bool valid) {
+  if (n0 < p.norm_cols) {
+    // ---- per-head RMSNorm (+ RoPE): one head = 128 accumulator columns, all owned by this thread ----
+    if constexpr (BN % 128 == 0) {
+#pragma unroll 1
+      for (int hc = 0; hc < BN; hc += 128) {
+        const int col0 = n0 + hc;
+        float v[128];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_x32f(taddr + hc + c * 32, v + c * 32);
+        tmem_wait_ld();
+        if (col0 < p.norm_cols) {
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
+          const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+          const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
+#pragma unroll
+          for (int j = 0; j < 128; j += 4) {
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
+            v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
+          }
+          if (col0 < p.rope_cols) {
+            const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
+            const float* cs = p.rope_cos + (long long)pos * 64;
+            const float* sn = p.rope_sin + (long long)pos * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + j));
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + j));
+              float a, b;
+              a = v[2 * j + 0]; b = v[2 * j + 1]; v[2 * j + 0] = a * c4.x - b * s4.x; v[2 * j + 1] = b * c4.x + a * s4.x;
+              a = v[2 * j + 2]; b = v[2 * j + 3]; v[2 * j + 2] = a * c4.y - b * s4.y; v[2 * j + 3] = b * c4.y + a * s4.y;
+              a = v[2 * j + 4]; b = v[2 * j + 5]; v[2 * j + 4] = a * c4.z - b * s4.z; v[2 * j + 5] = b * c4.z + a * s4.z;
+              a = v[2 * j + 6]; b = v[2 * j + 7]; v[2 * j + 6] = a * c4.w - b * s4.w; v[2 * j + 7] = b * c4.w + a * s4.w;
+            }
+          }
+        } else if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 128; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 128; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col0 + j, v + j);
+        }
+      }
+    }
+  } else {
+    // ---- plain epilogue in 32-column chunks ----
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld_x32f(taddr + c, v);
+      tmem_wait_ld();
+      finish_and_store<32>(p, v, drow, n0 + c, valid);
+    }
   }
 }
 
@@ -227,66 +294,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-
-      if (n0 < p.norm_cols) {
-        // ---- per-head RMSNorm (+ RoPE): one head = 128 accumulator columns, all owned by this thread ----
-        if constexpr (BN % 128 == 0) {
-#pragma unroll 1
-          for (int hc = 0; hc < BN; hc += 128) {
-            const int col0 = n0 + hc;
-            float v[128];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_x32f(taddr + hc + c * 32, v + c * 32);
-            tmem_wait_ld();
-            if (col0 < p.norm_cols) {
-              float ss = 0.f;
-#pragma unroll
-              for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
-              const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
-              const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
-#pragma unroll
-              for (int j = 0; j < 128; j += 4) {
-                const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
-                v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
-              }
-              if (col0 < p.rope_cols) {
-                const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
-                const float* cs = p.rope_cos + (long long)pos * 64;
-                const float* sn = p.rope_sin + (long long)pos * 64;
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                  const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + j));
-                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + j));
-                  float a, b;
-                  a = v[2 * j + 0]; b = v[2 * j + 1]; v[2 * j + 0] = a * c4.x - b * s4.x; v[2 * j + 1] = b * c4.x + a * s4.x;
-                  a = v[2 * j + 2]; b = v[2 * j + 3]; v[2 * j + 2] = a * c4.y - b * s4.y; v[2 * j + 3] = b * c4.y + a * s4.y;
-                  a = v[2 * j + 4]; b = v[2 * j + 5]; v[2 * j + 4] = a * c4.z - b * s4.z; v[2 * j + 5] = b * c4.z + a * s4.z;
-                  a = v[2 * j + 6]; b = v[2 * j + 7]; v[2 * j + 6] = a * c4.w - b * s4.w; v[2 * j + 7] = b * c4.w + a * s4.w;
-                }
-              }
-            } else if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 128; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-              }
-            }
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 128; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col0 + j, v + j);
-            }
-          }
-        }
-      } else {
-        // ---- plain epilogue in 32-column chunks ----
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          tmem_ld_x32f(taddr + c, v);
-          tmem_wait_ld();
-          finish_and_store<32>(p, v, drow, n0 + c, valid);
-        }
-      }
+      epilogue_tile<BN>(p, taddr, n0, row, drow, valid);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
@@ -298,6 +306,223 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+}
+
+
+static GemmParams make_params(const amb_gemm_args* a) {
+  GemmParams p;
+  p.M = a->m; p.N = a->n; p.K = a->k;
+  p.k_split_blocks = a->a2 ? a->k_split / BK : 0x7fffffff;
+  p.C = a->c; p.ldc = a->ldc; p.c_fp32 = a->c_fp32;
+  p.bias = a->bias;
+  p.residual = a->residual; p.ldr = a->ldr; p.res_fp32 = a->res_fp32;
+  p.act = a->act;
+  p.col_scale = a->col_scale;
+  p.grp_rows = a->grp_rows; p.grp_stride = a->grp_stride; p.row_off = a->row_off;
+  p.norm_cols = a->norm_cols; p.norm_seg = a->norm_seg;
+  p.norm_w0 = a->norm_w0; p.norm_w1 = a->norm_w1 ? a->norm_w1 : a->norm_w0;
+  p.norm_eps = a->norm_eps;
+  p.rope_cols = a->rope_cols; p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
+  p.rope_rows_per_pos = a->rope_rows_per_pos > 0 ? a->rope_rows_per_pos : 1;
+
+  return p;
+}
+
+// =====================================================================================================================
+// 2-CTA variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 output tile.  Each CTA
+// stages its own 128 rows of A and HALF of the W tile (128 of the 256 output columns' rows), so per k-block it moves
+// 32 KB instead of 48 KB through TMA / shared memory for the same MMA work — the single-CTA kernel is bound by
+// shared-memory bandwidth (MMA operand reads + TMA writes), not by the tensor pipe.  The leader CTA issues one
+// 256 x 256 x 16 MMA per UMMA_K step that reads both CTAs' shared memory and writes each CTA's 128 accumulator rows into
+// its own TMEM.  Barriers: `full` lives in the leader (both CTAs' TMA bytes are credited to it), `empty` / `tmem_full`
+// are signalled in both CTAs by multicast commits, `tmem_empty` collects both epilogues in the leader.
+// =====================================================================================================================
+template <int STAGES>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = BM * BK * 2;        // 16 KB: my 128 rows of A
+  static constexpr int B_BYTES = 128 * BK * 2;       // 16 KB: my half of the 256-row W tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using L = Gemm2Smem<STAGES>;
+  constexpr int BN = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2] (leader's copy is the live one: 256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tmem_full[a], 1);
+        mbar_init(&tmem_empty[a], 256);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_n_tiles = p.N / BN;
+  const int num_m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = num_n_tiles * num_m_pairs;
+  const int num_kb = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    int s = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m0 = (tile / num_n_tiles) * (2 * BM) + rank * BM;
+      const int nb = (tile % num_n_tiles) * BN + rank * 128;  // my half of the W tile rows
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        if (elect_one()) {
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::STAGE_BYTES);  // bytes of BOTH CTAs land on the leader's barrier
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (kb < p.k_split_blocks) tma_load_2d_pair(sa, &tmA, &full_bar[s], kb * BK, m0, kEvictNormal);
+          else tma_load_2d_pair(sa, &tmA2, &full_bar[s], (kb - p.k_split_blocks) * BK, m0, kEvictNormal);
+          tma_load_2d_pair(sb, &tmB, &full_bar[s], kb * BK, nb, kEvictLast);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, 0, 0);
+      int s = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t adesc = make_desc_kmajor_sw128(a_addr);
+          const uint64_t bdesc = make_desc_kmajor_sw128(a_addr + L::A_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) mma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            tc_commit_pair(&empty_bar[s]);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; phase ^= 1; }
+        }
+        if (elect_one()) tc_commit_pair(&tmem_full[acc]);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs; each CTA owns its 128 accumulator rows) =====================
+    const int quarter = warp & 3;
+    const int row_in_tile = quarter * 32 + lane;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m0 = (tile / num_n_tiles) * (2 * BM) + rank * BM;
+      const int n0 = (tile % num_n_tiles) * BN;
+      const int row = m0 + row_in_tile;
+      const bool valid = row < p.M;
+      long long drow = row;
+      if (p.grp_rows > 0) drow = (long long)(row / p.grp_rows) * p.grp_stride + (row % p.grp_rows) + p.row_off;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
+      epilogue_tile<BN>(p, taddr, n0, row, drow, valid);
+      tc_fence_before();
+      if (leader) mbar_arrive(&tmem_empty[acc]);
+      else mbar_arrive_remote(&tmem_empty[acc], 0);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA of the pair may free TMEM / exit while its peer still uses shared memory or TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int STAGES>
+static int launch_gemm2(const amb_gemm_args* a, cudaStream_t stream) {
+  using L = Gemm2Smem<STAGES>;
+  CUtensorMap tmA, tmA2, tmB;
+  const int k1 = (a->a2 != nullptr) ? a->k_split : a->k;
+  {
+    uint64_t dims[2] = {(uint64_t)k1, (uint64_t)a->m};
+    uint64_t str[1] = {(uint64_t)a->lda * 2};
+    uint32_t box[2] = {BK, BM};
+    int r = encode_tmap_bf16(&tmA, a->a, 2, dims, str, box);
+    if (r) return r;
+  }
+  if (a->a2) {
+    uint64_t dims[2] = {(uint64_t)(a->k - a->k_split), (uint64_t)a->m};
+    uint64_t str[1] = {(uint64_t)a->lda2 * 2};
+    uint32_t box[2] = {BK, BM};
+    int r = encode_tmap_bf16(&tmA2, a->a2, 2, dims, str, box);
+    if (r) return r;
+  } else {
+    tmA2 = tmA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)a->k, (uint64_t)a->n};
+    uint64_t str[1] = {(uint64_t)a->ldw * 2};
+    uint32_t box[2] = {BK, 128};
+    int r = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box);
+    if (r) return r;
+  }
+  GemmParams p = make_params(a);
+  auto kern = gemm2_bf16_kernel<STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    attr_set = true;
+  }
+  const int num_tiles = (a->n / 256) * ((a->m + 2 * BM - 1) / (2 * BM));
+  int clusters = num_sms() / 2;
+  if (clusters > num_tiles) clusters = num_tiles;
+  kern<<<2 * clusters, 192, L::TOTAL, stream>>>(tmA, tmA2, tmB, p);  // cluster dims are compiled in (__cluster_dims__)
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
 }
 
 template <int BN, int STAGES>
@@ -328,21 +553,7 @@ static int launch_gemm(const amb_gemm_args* a, cudaStream_t stream) {
     int r = encode_tmap_bf16(&tmB, a->w, 2, dims, str, box);
     if (r) return r;
   }
-  GemmParams p;
-  p.M = a->m; p.N = a->n; p.K = a->k;
-  p.k_split_blocks = a->a2 ? a->k_split / BK : 0x7fffffff;
-  p.C = a->c; p.ldc = a->ldc; p.c_fp32 = a->c_fp32;
-  p.bias = a->bias;
-  p.residual = a->residual; p.ldr = a->ldr; p.res_fp32 = a->res_fp32;
-  p.act = a->act;
-  p.col_scale = a->col_scale;
-  p.grp_rows = a->grp_rows; p.grp_stride = a->grp_stride; p.row_off = a->row_off;
-  p.norm_cols = a->norm_cols; p.norm_seg = a->norm_seg;
-  p.norm_w0 = a->norm_w0; p.norm_w1 = a->norm_w1 ? a->norm_w1 : a->norm_w0;
-  p.norm_eps = a->norm_eps;
-  p.rope_cols = a->rope_cols; p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
-  p.rope_rows_per_pos = a->rope_rows_per_pos > 0 ? a->rope_rows_per_pos : 1;
-
+  GemmParams p = make_params(a);
   auto kern = gemm_bf16_kernel<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -379,6 +590,8 @@ extern "C" int amb_gemm_bf16(const amb_gemm_args* a, amb_stream_t stream) {
     AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale, "gemm: head epilogue excludes residual/activation/col_scale");
   }
   cudaStream_t s = (cudaStream_t)stream;
+  static const int two_cta = []() { const char* e = getenv("AMB_GEMM_2CTA"); return e ? atoi(e) : 1; }();  // 2-CTA kernel is the product path for N % 256 == 0
+  if (two_cta && a->n % 256 == 0 && a->m >= 256) return launch_gemm2<6>(a, s);
   if (a->n % 256 == 0) return launch_gemm<256, 4>(a, s);
   if (a->n % 128 == 0) return launch_gemm<128, 6>(a, s);
   return launch_gemm<64, 8>(a, s);
