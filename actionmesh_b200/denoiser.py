@@ -258,7 +258,7 @@ class B200Denoiser:
         }
         if world > 1:  # frame-sharded window: local [K|V] rows and the all-gathered buffer (one chunk per rank)
             ws["kv_local"] = torch.empty(M, 2 * c.width, dtype=bf, device=dev)
-            ws["kv_all"] = torch.empty(world, M, 2 * c.width, dtype=bf, device=dev)
+            ws["kv_all"] = torch.empty(B, world, T * L, 2 * c.width, dtype=bf, device=dev)
         self._ws = {key: ws}  # keep one shape resident
         return ws
 
@@ -365,20 +365,27 @@ class B200Denoiser:
             if shard is not None and shard.world > 1 and inflated:
                 # frame-sharded window: K/V of this rank's frames -> NCCL all-gather -> attention over `world` chunks;
                 # the Q projection runs while the gather is in flight.
-                from .window_shard import chunked_kv_views
                 import torch.distributed as dist
                 kv_local, kv_all = ws["kv_local"], ws["kv_all"]
                 ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
                                    sin=st.rope_sin, rows_per_pos=L))
-                work = dist.all_gather_into_tensor(kv_all.view(-1, 2 * D), kv_local, group=shard.group, async_op=True)
+                # one all-gather per CFG branch (contiguous row blocks), so the attention of branch b overlaps the
+                # gather of branch b+1; kv_all is (B, world, T_local*L, 2D): chunk c of a branch = rank c's frames
+                TLl = T * L
+                works = [dist.all_gather_into_tensor(kv_all[b].view(-1, 2 * D), kv_local[b * TLl:(b + 1) * TLl],
+                                                     group=shard.group, async_op=True) for b in range(B)]
                 ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
                                    sin=st.rope_sin, rows_per_pos=L))
-                work.wait()
-                k5, v5 = chunked_kv_views(kv_all, B, T * L, H, dh)
-                q4 = qkv[:, 0:D].unflatten(0, (B, T * L)).unflatten(-1, (H, dh))
-                ops.flash_attn(q4, k5, v5, att.view(B, T * L, H, dh), scale, kv_chunks=shard.world, tag="attn_self")
+                for b in range(B):
+                    works[b].wait()
+                    kvb = kv_all[b]                                              # (world, TLl, 2D)
+                    k5 = kvb[None, :, :, 0:D].unflatten(-1, (H, dh))             # (1, world, TLl, H, dh)
+                    v5 = kvb[None, :, :, D:2 * D].unflatten(-1, (H, dh))
+                    q4 = qkv[b * TLl:(b + 1) * TLl, 0:D].unflatten(-1, (H, dh))[None]
+                    ops.flash_attn(q4, k5, v5, att[b * TLl:(b + 1) * TLl].view(1, TLl, H, dh), scale,
+                                   kv_chunks=shard.world, tag="attn_self")
             else:
                 ops.gemm(xn, w[p + "s.qkv"], qkv,
                          norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,

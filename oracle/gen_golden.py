@@ -88,6 +88,30 @@ def main():
     outw, _ = mw.forward(hidden_states=h_in, context=c_in, framestep=f_in, diffusion_time=t, mask=m_in)
     torch.save({"config": WIDE, "seed": 77, "input_seed": 6, "forward_out": outw, "t": t},
                os.path.join(GOLD, "denoiser_wide3.pt"))
+    # ---- Stage-II decoder (test-side only: turns latents into vertices for the Chamfer metric) + ActionBench Chamfer
+    import importlib.util
+
+    from actionmesh.model.temporal_autoencoder import ActionMeshAutoencoder
+    from oracle import autoencoder_oracle as ao
+
+    acfg = dict(width=256, num_layers=2, num_attention_heads=2)
+    ae = ActionMeshAutoencoder(verbose=False, **acfg).eval()
+    ae.load_state_dict(ao.make_autoencoder_state_dict(ao.AutoencoderConfig(**acfg), 4321), strict=True)
+    gg = torch.Generator().manual_seed(0)
+    lat = torch.randn(1, 3, 7, 64, generator=gg)
+    fsx = torch.tensor([[2.0, 3.0, 4.0]])
+    sa, ta = torch.tensor([0.0]), torch.tensor([[0.0, 0.5, 1.0]])
+    qv = torch.rand(1, 50, 6, generator=gg) * 2 - 1
+    disp = ae.forward(lat, fsx, sa, ta, qv)
+    spec = importlib.util.spec_from_file_location("ref_chamfer", os.path.join(reference_loader.REFERENCE_ROOT, "actionbench", "chamfer.py"))
+    ch = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ch)
+    pa, pb = torch.rand(500, 3, generator=gg).numpy(), torch.rand(600, 3, generator=gg).numpy()
+    torch.save({"config": acfg, "seed": 4321, "latent": lat, "framestep": fsx, "source_alpha": sa, "target_alphas": ta,
+                "query": qv, "displacement": disp, "chamfer_a": pa, "chamfer_b": pb,
+                "chamfer_n300": ch.compute_chamfer_score(pa, pb, n=300), "chamfer_all": ch.compute_chamfer_score(pa, pb, n=0)},
+               os.path.join(GOLD, "autoencoder_tiny.pt"))
+
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))
 

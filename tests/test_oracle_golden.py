@@ -83,6 +83,21 @@ def test_wide3_forward_matches_reference_output():
     assert (out - g["forward_out"]).abs().max() < 5e-5
 
 
+def test_stage2_decoder_and_chamfer_match_reference_outputs():
+    """The test-side Stage-II decoder (latents -> vertex displacements) and the Chamfer metric restatement reproduce the
+    reference's ActionMeshAutoencoder.forward and actionbench/chamfer.py outputs stored in the fixture."""
+    from oracle import autoencoder_oracle as ao
+
+    g = load_golden("autoencoder_tiny.pt")
+    cfg = ao.AutoencoderConfig(**g["config"])
+    sd = ao.make_autoencoder_state_dict(cfg, g["seed"])
+    out = ao.autoencoder_forward(sd, cfg, g["latent"], g["framestep"], g["source_alpha"], g["target_alphas"], g["query"])
+    assert out.shape == g["displacement"].shape and (out - g["displacement"]).abs().max() < 1e-5
+    assert abs(ao.chamfer_score(g["chamfer_a"], g["chamfer_b"], n=300) - g["chamfer_n300"]) < 1e-12
+    assert abs(ao.chamfer_score(g["chamfer_a"], g["chamfer_b"], n=0) - g["chamfer_all"]) < 1e-12
+    assert ao.chamfer_score(g["chamfer_a"], g["chamfer_a"], n=0) == 0.0
+
+
 @pytest.mark.skipif(not reference_loader.available(), reason="reference checkout not present (GPU box)")
 def test_oracle_matches_live_reference_modules():
     ns = reference_loader.load()
