@@ -10,11 +10,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libactionmesh_b200.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 EXPORTS = [
     "amb_last_error", "amb_abi_version", "amb_device_info", "amb_cfg_euler_step", "amb_layernorm",
-    "amb_cast_f32_bf16", "amb_patchify", "amb_timestep_embedding", "amb_add_bias_rows", "amb_gemm_bf16", "amb_flash_attn_fwd", "amb_debug_set_attn_trace",
+    "amb_cast_f32_bf16", "amb_patchify", "amb_timestep_embedding", "amb_alpha_rows", "amb_point_embedding",
+    "amb_displacement_out", "amb_add_bias_rows", "amb_gemm_bf16", "amb_flash_attn_fwd", "amb_debug_set_attn_trace",
 ]
 
 
@@ -82,6 +83,9 @@ def load_library() -> C.CDLL:
         C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int,
         C.c_float, C.c_void_p,
     ]
+    lib.amb_alpha_rows.argtypes = [C.c_float, C.c_float, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+    lib.amb_point_embedding.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.amb_displacement_out.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.amb_patchify.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.amb_cast_f32_bf16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.amb_timestep_embedding.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

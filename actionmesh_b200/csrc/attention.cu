@@ -320,686 +320,19 @@ flash_attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 }
 
 
-// =====================================================================================================================
-// v2 (head_dim 128): 128-key K/V tiles, P kept in TMEM (aliasing S, consumed by a TS-form MMA), P handed over in two
-// halves so the P·V MMAs of the first 64 keys overlap the exponentials of the last 64.
-//   warps 0-3  softmax warpgroup, query tile 0      warps 4-7  softmax warpgroup, query tile 1
-//   warp 8     TMA producer (Q once; K ring, V ring) warp 9     MMA issuer + TMEM owner
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i = bf16 pairs in columns [0,64) of S_i.
-// Tensor-pipe order:  S0 S1 | PV0a PV0b S0' | PV1a PV1b S1' | ...
-// =====================================================================================================================
-constexpr int V2_BK = 128;
-constexpr int V2_THREADS = 320;
-
-template <int KSTAGES, int VSTAGES>
-struct AttnV2Smem {
-  static constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KB: two 64-column halves of [128 rows x 128 B]
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = 2 * TILE_BYTES;
-  static constexpr int V_OFF = K_OFF + KSTAGES * TILE_BYTES;
-  static constexpr int BAR_OFF = V_OFF + VSTAGES * TILE_BYTES;
-  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 2 + 2 + 2 + 2;
-  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
-};
-
-// EMU: every EMU-th pair of exponentials runs on the FMA pipes (0 = none).  SEQ: the two softmax warpgroups take turns
-// in the MUFU-bound exponential section (named barriers), which staggers them so that one warpgroup's softmax overlaps
-// the other tile's MMAs instead of both contending for the MUFU and then both waiting on the tensor pipe.
-template <int KSTAGES, int VSTAGES, int EMU, bool SEQ>
-__global__ void __launch_bounds__(V2_THREADS, 1)
-flash_attn_fwd_v2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using L = AttnV2Smem<KSTAGES, VSTAGES>;
-  constexpr int D = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* k_full = q_full + 1;
-  uint64_t* k_empty = k_full + KSTAGES;
-  uint64_t* v_full = k_empty + KSTAGES;
-  uint64_t* v_empty = v_full + VSTAGES;
-  uint64_t* s_full = v_empty + VSTAGES;  // [2]
-  uint64_t* p_a = s_full + 2;            // [2] first 64 keys of P ready
-  uint64_t* p_b = p_a + 2;               // [2] last 64 keys of P ready
-  uint64_t* o_full = p_b + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath for role code)
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * ATT_BQ);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int tiles_per_chunk = (p.sk_chunk + V2_BK - 1) / V2_BK;
-  const int n_kv = p.kv_chunks * tiles_per_chunk;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 9) {
-    if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1);
-        mbar_init(&p_a[i], 128);
-        mbar_init(&p_b[i], 128);
-        mbar_init(&o_full[i], 1);
-      }
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp >= 8) {
-  if (warp == 8) {
-    // ===================== TMA producer (warp converged, one elected lane issues) =====================
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * L::TILE_BYTES);
-      for (int i = 0; i < 2; ++i)
-        for (int c = 0; c < 2; ++c)
-          tma_load_4d(smem + L::Q_OFF + i * L::TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
-                      batch, kEvictFirst);
-    }
-    __syncwarp();
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      const int chunk = j / tiles_per_chunk;
-      const int key0 = (j - chunk * tiles_per_chunk) * V2_BK;
-      mbar_wait(&k_empty[ks], kph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&k_full[ks], L::TILE_BYTES);
-        uint8_t* sk = smem + L::K_OFF + ks * L::TILE_BYTES;
-        tma_load_5d(sk, &tmK, &k_full[ks], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sk + 16384, &tmK, &k_full[ks], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-      mbar_wait(&v_empty[vs], vph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&v_full[vs], L::TILE_BYTES);
-        uint8_t* sv = smem + L::V_OFF + vs * L::TILE_BYTES;
-        tma_load_5d(sv, &tmV, &v_full[vs], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sv + 16384, &tmV, &v_full[vs], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-    }
-  } else if (warp == 9) {
-    // ===================== MMA issuer (warp converged; descriptors stay in uniform registers) =====================
-    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V2_BK, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
-    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
-    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
-    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
-
-    auto issue_qk = [=](int i, int kstage) {
-      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::TILE_BYTES);
-      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::TILE_BYTES);
-      const uint32_t d = tmem_base + i * 128;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k) {
-          const uint32_t off = (k >> 2) * (16384 / 16) + (k & 3) * 2;  // descriptor address field is (bytes >> 4)
-          mma_ss(d, qd + off, kd + off, idesc_qk, k != 0);
-        }
-        tc_commit(&s_full[i]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv_half = [=](int i, int vstage, int half, bool first_tile) {
-      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::TILE_BYTES, 16384);
-      const uint32_t d = tmem_base + 256 + i * 128;
-      const uint32_t pa = tmem_base + i * 128;  // P aliases S_i: 16 keys = 8 columns
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const int k = half * 4 + kk;
-          mma_ts(d, pa + k * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);  // 16 keys = 2048 B
-        }
-      }
-      __syncwarp();
-    };
-    auto commit = [=](uint64_t* bar) {
-      if (elect_one()) tc_commit(bar);
-      __syncwarp();
-    };
-
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    issue_qk(1, 0);
-    commit(&k_empty[0]);
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      int ks_next = ks + 1;
-      uint32_t kph_next = kph;
-      if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
-      const bool has_next = (j + 1 < n_kv);
-      const uint32_t par = j & 1;
-      mbar_wait(&v_full[vs], vph);
-      // ---- tile 0
-      mbar_wait(&p_a[0], par);
-      tc_fence_after();
-      issue_pv_half(0, vs, 0, j == 0);
-      mbar_wait(&p_b[0], par);
-      tc_fence_after();
-      issue_pv_half(0, vs, 1, j == 0);
-      if (has_next) {
-        mbar_wait(&k_full[ks_next], kph_next);
-        tc_fence_after();
-        issue_qk(0, ks_next);
-      } else {
-        commit(&o_full[0]);
-      }
-      // ---- tile 1
-      mbar_wait(&p_a[1], par);
-      tc_fence_after();
-      issue_pv_half(1, vs, 0, j == 0);
-      mbar_wait(&p_b[1], par);
-      tc_fence_after();
-      issue_pv_half(1, vs, 1, j == 0);
-      commit(&v_empty[vs]);
-      if (has_next) {
-        issue_qk(1, ks_next);
-        commit(&k_empty[ks_next]);
-      } else {
-        commit(&o_full[1]);
-      }
-      ks = ks_next;
-      kph = kph_next;
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-    }
-  }
-  } else {
-    // ===================== softmax warpgroups =====================
-    const int wg = warp >> 2;
-    const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
-    const int q_row = q0 + wg * ATT_BQ + row_in_tile;
-    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + wg * 128 + lane_sel;
-    const uint32_t o_addr = tmem_base + 256 + wg * 128 + lane_sel;
-
-    float m_used = -INFINITY;
-    float row_sum = 0.f;
-    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V2_BK;
-
-    // One key-tile step.  MASKED is a compile-time flag: only the last (partial) tile of a chunk carries the tail
-    // masking code, so the hot path has no per-element select.
-    auto softmax_step = [&](int j, auto masked_tag) {
-      constexpr bool MASKED = decltype(masked_tag)::value;
-      mbar_wait(&s_full[wg], j & 1);
-      tc_fence_after();
-      if (EMU == 8) {  // timing experiment only (AMB_ATTN_EMU=8): tensor pipe + barriers alone, no softmax work
-        tc_fence_before();
-        mbar_arrive(&p_a[wg]);
-        mbar_arrive(&p_b[wg]);
-        row_sum = 1.f;
-        return;
-      }
-      // ---- one TMEM read of the 128 scores of this row (4 back-to-back loads, one wait)
-      float sc[V2_BK];
-      tmem_ld_x32f(s_addr, sc);
-      tmem_ld_x32f(s_addr + 32, sc + 32);
-      tmem_ld_x32f(s_addr + 64, sc + 64);
-      tmem_ld_x32f(s_addr + 96, sc + 96);
-      tmem_wait_ld();
-      if (MASKED) {
-#pragma unroll
-        for (int t = 0; t < V2_BK; ++t)
-          if (t >= last_valid) sc[t] = -INFINITY;
-      }
-      float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
-#pragma unroll
-      for (int t = 4; t < V2_BK; t += 4) {
-        mx0 = fmaxf(mx0, fmaxf(sc[t], sc[t + 1]));
-        mx1 = fmaxf(mx1, fmaxf(sc[t + 2], sc[t + 3]));
-      }
-      const float mx = fmaxf(mx0, mx1);
-      const float m_new = fmaxf(m_used, mx);
-      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
-      if (j == 0) {
-        m_used = m_new;
-      } else if (__any_sync(0xffffffffu, need)) {
-        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
-        if (need) {
-          m_used = m_new;
-          row_sum *= alpha;
-        }
-#pragma unroll 1
-        for (int c = 0; c < D; c += 32) {
-          float ov[32];
-          tmem_ld_x32f(o_addr + c, ov);
-          tmem_wait_ld();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
-          tmem_st_x32f(o_addr + c, ov);
-        }
-        tmem_wait_st();
-      }
-      // ---- exponentials; bf16 P written over the consumed S columns, handed to the MMA warp in two halves
-      if (SEQ && (wg == 1 || j > 0)) named_bar_sync(1 + wg, 256);  // my turn on the MUFU (warpgroup 0 goes first)
-      const float mb = m_used * p.scale_log2;
-      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
-      uint64_t psum2 = pk2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float x0, x1, e0, e1;
-          upk2(fma2(pk2(sc[c * 32 + t], sc[c * 32 + t + 1]), scale2, nmb2), x0, x1);
-          if (EMU == 9) {  // timing experiment only (AMB_ATTN_EMU=9): no exponentials, wrong numerics
-            e0 = x0;
-            e1 = x1;
-          } else if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
-            exp2_poly2(x0, x1, e0, e1);
-          } else {
-            e0 = ex2_approx(x0);  // exp2(-inf) = 0 masks the tail
-            e1 = ex2_approx(x1);
-          }
-          psum2 = add2(psum2, pk2(e0, e1));
-          pk[t >> 1] = pack_bf16(e0, e1);
-        }
-        tmem_st_x16(s_addr + c * 16, pk);
-        if (c == 1) {
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(&p_a[wg]);
-        }
-      }
-      if (SEQ && !(wg == 1 && j + 1 == n_kv)) named_bar_arrive(2 - wg, 256);  // hand the MUFU to the other warpgroup
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_b[wg]);
-      {
-        float s0, s1;
-        upk2(psum2, s0, s1);
-        row_sum += s0 + s1;
-      }
-    };
-
-    const bool has_tail = last_valid < V2_BK;
-    int jj = 0;  // tile index inside the current K/V chunk (kept incrementally: no integer division in the loop)
-    for (int j = 0; j < n_kv; ++j) {
-      const bool tail = has_tail && (jj == tiles_per_chunk - 1);
-      if (++jj == tiles_per_chunk) jj = 0;
-      if (tail) softmax_step(j, std::true_type{});
-      else softmax_step(j, std::false_type{});
-    }
-
-    mbar_wait(&o_full[wg], 0);
-    tc_fence_after();
-    const float inv = 1.0f / row_sum;
-    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + (long long)q_row * p.o_stride_s;
-#pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
-      float ov[32];
-      tmem_ld_x32f(o_addr + c, ov);
-      tmem_wait_ld();
-      if (q_row < p.sq) {
-#pragma unroll
-        for (int t = 0; t < 32; t += 8) {
-          uint4 pk;
-          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
-          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
-          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
-          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
-          *reinterpret_cast<uint4*>(orow + c + t) = pk;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
+constexpr int V2_BK = 128;  // keys per K/V tile of the v4 kernel
 
 // =====================================================================================================================
-// v3 (head_dim 128): 64-key granularity with DOUBLE-BUFFERED S per query tile.  The QK^T of key tile j+2 is issued as
-// soon as P·V of tile j has been issued, so a softmax warpgroup always finds its next S tile ready (it never waits on
-// the tensor pipe) and the tensor pipe always has two S tiles of slack per query tile.  P (bf16) aliases its S buffer.
-// TMEM: S[i][b] = columns (2i+b)*64 (+64),  O[i] = 256 + 128 i.       i = query tile, b = j & 1.
-// Tensor-pipe order: S00 S10 S01 S11 | PV0(0) S0(2) PV1(0) S1(2) | PV0(1) S0(3) PV1(1) S1(3) | ...
-// =====================================================================================================================
-constexpr int V3_BK = 64;
-constexpr int V3_THREADS = 320;
-
-template <int KSTAGES, int VSTAGES>
-struct AttnV3Smem {
-  static constexpr int Q_TILE_BYTES = 128 * 128 * 2;   // 32 KB
-  static constexpr int KV_TILE_BYTES = V3_BK * 128 * 2;  // 16 KB: two d-halves of [64 keys x 128 B]
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = 2 * Q_TILE_BYTES;
-  static constexpr int V_OFF = K_OFF + KSTAGES * KV_TILE_BYTES;
-  static constexpr int BAR_OFF = V_OFF + VSTAGES * KV_TILE_BYTES;
-  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 4 + 4 + 2 + 2;
-  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
-};
-
-template <int KSTAGES, int VSTAGES, int EMU>
-__global__ void __launch_bounds__(V3_THREADS, 1)
-flash_attn_fwd_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using L = AttnV3Smem<KSTAGES, VSTAGES>;
-  constexpr int D = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* k_full = q_full + 1;
-  uint64_t* k_empty = k_full + KSTAGES;
-  uint64_t* v_full = k_empty + KSTAGES;
-  uint64_t* v_empty = v_full + VSTAGES;
-  uint64_t* s_full = v_empty + VSTAGES;  // [tile][buf] -> index 2*tile + buf
-  uint64_t* p_ready = s_full + 4;        // [tile][buf]
-  uint64_t* pv_done = p_ready + 4;       // [tile]: completes once per P·V (guards the rare O rescale)
-  uint64_t* o_full = pv_done + 2;        // [tile]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform (uniform datapath for role code)
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * ATT_BQ);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int tiles_per_chunk = (p.sk_chunk + V3_BK - 1) / V3_BK;
-  const int n_kv = p.kv_chunks * tiles_per_chunk;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 9) {
-    if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-      for (int i = 0; i < 4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); }
-      for (int i = 0; i < 2; ++i) { mbar_init(&pv_done[i], 1); mbar_init(&o_full[i], 1); }
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 8) {
-    // ===================== TMA producer (warp converged, one elected lane issues) =====================
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * L::Q_TILE_BYTES);
-      for (int i = 0; i < 2; ++i)
-        for (int c = 0; c < 2; ++c)
-          tma_load_4d(smem + L::Q_OFF + i * L::Q_TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
-                      batch, kEvictFirst);
-    }
-    __syncwarp();
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
-    // K runs two tiles ahead of V (the QK^T look-ahead); issue order K0 K1 | V0 K2 | V1 K3 | ...
-    // (lambdas capture POINTERS to the __grid_constant__ tensor maps: a by-value copy would live in local memory,
-    //  which TMA cannot read)
-    const CUtensorMap* pK = &tmK;
-    const CUtensorMap* pV = &tmV;
-    auto load_k = [=](int j, int stage, uint32_t ph) {
-      const int chunk = j / tiles_per_chunk;
-      const int key0 = (j - chunk * tiles_per_chunk) * V3_BK;
-      mbar_wait(&k_empty[stage], ph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&k_full[stage], L::KV_TILE_BYTES);
-        uint8_t* sk = smem + L::K_OFF + stage * L::KV_TILE_BYTES;
-        tma_load_5d(sk, pK, &k_full[stage], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sk + 8192, pK, &k_full[stage], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-    };
-    auto load_v = [=](int j, int stage, uint32_t ph) {
-      const int chunk = j / tiles_per_chunk;
-      const int key0 = (j - chunk * tiles_per_chunk) * V3_BK;
-      mbar_wait(&v_empty[stage], ph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&v_full[stage], L::KV_TILE_BYTES);
-        uint8_t* sv = smem + L::V_OFF + stage * L::KV_TILE_BYTES;
-        tma_load_5d(sv, pV, &v_full[stage], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sv + 8192, pV, &v_full[stage], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-    };
-    for (int j = 0; j < 2 && j < n_kv; ++j) {
-      load_k(j, ks, kph);
-      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      load_v(j, vs, vph);
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-      if (j + 2 < n_kv) {
-        load_k(j + 2, ks, kph);
-        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-      }
-    }
-  } else if (warp == 9) {
-    // ===================== MMA issuer (warp converged; descriptors stay in uniform registers) =====================
-    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V3_BK, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
-    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
-    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
-    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
-
-    auto issue_qk = [=](int i, int buf, int kstage) {
-      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::Q_TILE_BYTES);
-      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::KV_TILE_BYTES);
-      const uint32_t d = tmem_base + (2 * i + buf) * 64;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_ss(d, qd + ((k >> 2) * (16384 / 16) + (k & 3) * 2), kd + ((k >> 2) * (8192 / 16) + (k & 3) * 2), idesc_qk, k != 0);
-        tc_commit(&s_full[2 * i + buf]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [=](int i, int buf, int vstage, bool first_tile) {
-      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::KV_TILE_BYTES, 8192);
-      const uint32_t d = tmem_base + 256 + i * 128;
-      const uint32_t pa = tmem_base + (2 * i + buf) * 64;  // P aliases S[i][buf]: 16 keys = 8 columns
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < V3_BK / 16; ++k)
-          mma_ts(d, pa + k * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);
-        tc_commit(&pv_done[i]);
-      }
-      __syncwarp();
-    };
-    auto commit = [=](uint64_t* bar) {
-      if (elect_one()) tc_commit(bar);
-      __syncwarp();
-    };
-
-    mbar_wait(q_full, 0);
-    int ks = 0, vs = 0;       // stage of K tile (j+2) / V tile j
-    uint32_t kph = 0, vph = 0;
-    // prologue: S[.][0] from K0, S[.][1] from K1
-    for (int j = 0; j < 2 && j < n_kv; ++j) {
-      mbar_wait(&k_full[ks], kph);
-      tc_fence_after();
-      issue_qk(0, j, ks);
-      issue_qk(1, j, ks);
-      commit(&k_empty[ks]);
-      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-    }
-    for (int j = 0; j < n_kv; ++j) {
-      const int buf = j & 1;
-      const uint32_t par = (j >> 1) & 1;
-      const bool has_next = (j + 2 < n_kv);
-      mbar_wait(&v_full[vs], vph);
-      if (has_next) mbar_wait(&k_full[ks], kph);
-      // ---- tile 0
-      mbar_wait(&p_ready[0 + buf], par);
-      tc_fence_after();
-      issue_pv(0, buf, vs, j == 0);
-      if (has_next) issue_qk(0, buf, ks);
-      if (j + 1 == n_kv) commit(&o_full[0]);
-      // ---- tile 1
-      mbar_wait(&p_ready[2 + buf], par);
-      tc_fence_after();
-      issue_pv(1, buf, vs, j == 0);
-      commit(&v_empty[vs]);
-      if (has_next) {
-        issue_qk(1, buf, ks);
-        commit(&k_empty[ks]);
-        if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-      }
-      if (j + 1 == n_kv) commit(&o_full[1]);
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-    }
-  } else {
-    // ===================== softmax warpgroups =====================
-    const int wg = warp >> 2;
-    const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
-    const int q_row = q0 + wg * ATT_BQ + row_in_tile;
-    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t o_addr = tmem_base + 256 + wg * 128 + lane_sel;
-
-    float m_used = -INFINITY;
-    float row_sum = 0.f;
-    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V3_BK;
-
-    for (int j = 0; j < n_kv; ++j) {
-      const int buf = j & 1;
-      const uint32_t s_addr = tmem_base + (2 * wg + buf) * 64 + lane_sel;
-      mbar_wait(&s_full[2 * wg + buf], (j >> 1) & 1);
-      tc_fence_after();
-      float sc[V3_BK];
-      tmem_ld_x32f(s_addr, sc);
-      tmem_ld_x32f(s_addr + 32, sc + 32);
-      tmem_wait_ld();
-      const int jj = j % tiles_per_chunk;
-      if (jj == tiles_per_chunk - 1 && last_valid < V3_BK) {
-#pragma unroll
-        for (int t = 0; t < V3_BK; ++t)
-          if (t >= last_valid) sc[t] = -INFINITY;
-      }
-      float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
-#pragma unroll
-      for (int t = 4; t < V3_BK; t += 4) {
-        mx0 = fmaxf(mx0, fmaxf(sc[t], sc[t + 1]));
-        mx1 = fmaxf(mx1, fmaxf(sc[t + 2], sc[t + 3]));
-      }
-      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1));
-      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
-      if (j == 0) {
-        m_used = m_new;
-      } else if (__any_sync(0xffffffffu, need)) {
-        // rare: rescale O.  P·V of tile j-1 must have landed first (QK^T of tile j was issued before it).
-        mbar_wait(&pv_done[wg], (j - 1) & 1);
-        tc_fence_after();
-        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
-        if (need) {
-          m_used = m_new;
-          row_sum *= alpha;
-        }
-#pragma unroll 1
-        for (int c = 0; c < D; c += 32) {
-          float ov[32];
-          tmem_ld_x32f(o_addr + c, ov);
-          tmem_wait_ld();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
-          tmem_st_x32f(o_addr + c, ov);
-        }
-        tmem_wait_st();
-      }
-      const float mb = m_used * p.scale_log2;
-      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
-      uint64_t psum2 = pk2(0.f, 0.f);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float x0, x1, e0, e1;
-          upk2(fma2(pk2(sc[c * 32 + t], sc[c * 32 + t + 1]), scale2, nmb2), x0, x1);
-          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
-            exp2_poly2(x0, x1, e0, e1);
-          } else {
-            e0 = ex2_approx(x0);
-            e1 = ex2_approx(x1);
-          }
-          psum2 = add2(psum2, pk2(e0, e1));
-          pk[t >> 1] = pack_bf16(e0, e1);
-        }
-        tmem_st_x16(s_addr + c * 16, pk);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_ready[2 * wg + buf]);
-      {
-        float s0, s1;
-        upk2(psum2, s0, s1);
-        row_sum += s0 + s1;
-      }
-    }
-
-    mbar_wait(&o_full[wg], 0);
-    tc_fence_after();
-    const float inv = 1.0f / row_sum;
-    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + (long long)q_row * p.o_stride_s;
-#pragma unroll 1
-    for (int c = 0; c < D; c += 32) {
-      float ov[32];
-      tmem_ld_x32f(o_addr + c, ov);
-      tmem_wait_ld();
-      if (q_row < p.sq) {
-#pragma unroll
-        for (int t = 0; t < 32; t += 8) {
-          uint4 pk;
-          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
-          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
-          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
-          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
-          *reinterpret_cast<uint4*>(orow + c + t) = pk;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-
-// =====================================================================================================================
-// v4 (head_dim 128): v2's data flow (128-key tiles, P in TMEM, TS-form P·V, P handed over in two halves) with TWO threads
+// v4 (head_dim 128, the product kernel): 128-key K/V tiles, P kept in TMEM (aliasing S, consumed by a TS-form MMA), P
+// handed to the MMA warp in two halves so P·V of keys 0-63 overlaps the exponentials of keys 64-127, and TWO threads
 // per query row.  16 softmax warps: for query tile i, warps 8i..8i+3 own keys 0-63 of every 128-key tile and warps
 // 8i+4..8i+7 own keys 64-127 (a warp may only touch TMEM lanes 32*(warp%4)+[0,32), so both halves cover all 4 lane
 // quarters).  Halving the per-thread work halves the softmax latency on the critical QK -> softmax -> PV chain and gives
 // every SM sub-partition 4 softmax warps to interleave.  The two halves of a row exchange their partial row maxima
 // through shared memory (one 256-thread named barrier per tile step); partial row sums are combined once at the end.
-//   warp 16 = TMA producer, warp 17 = MMA issuer + TMEM owner.       TMEM as in v2.
+//   warp 16 = TMA producer, warp 17 = MMA issuer + TMEM owner.
+//   TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512); P_i = bf16 pairs in the first 32 columns of each key-half of S_i.
+//   Tensor-pipe order:  S0 S1 | PV0a PV0b S0' | PV1a PV1b S1' | ...
 // =====================================================================================================================
 constexpr int V4_THREADS = 576;
 
@@ -1293,7 +626,7 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         for (int t = 0; t < 16; t += 2) {
           float x0, x1, e0, e1;
           upk2(fma2(pk2(sc[t], sc[t + 1]), scale2, nmb2), x0, x1);
-          if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+          if (EMU > 0 && ((t >> 1) % (EMU > 0 ? EMU : 1)) == EMU - 1) {
             exp2_poly2(x0, x1, e0, e1);
           } else {
             e0 = ex2_approx(x0);
@@ -1638,7 +971,7 @@ flash_attn_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
       for (int t = 0; t < 40; t += 2) {
         float x0, x1, e0, e1;
         upk2(fma2(pk2(sc[t], sc[t + 1]), scale2, nmb2), x0, x1);
-        if (EMU > 0 && ((t >> 1) % EMU) == EMU - 1) {
+        if (EMU > 0 && ((t >> 1) % (EMU > 0 ? EMU : 1)) == EMU - 1) {
           exp2_poly2(x0, x1, e0, e1);
         } else {
           e0 = ex2_approx(x0);  // exp2(-inf) = 0 masks the tail
@@ -1705,15 +1038,12 @@ flash_attn_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
   }
 }
 
-template <int D, int STAGES, int VER>  // VER: 1 = v1 (any head_dim), 2 = v2, 3 = v3 (head_dim 128)
+template <int D, int STAGES, int VER>  // VER: 1 = baseline kernel (head_dim 64 or 128), 4 = product kernel, 5 = 80-key variant (head_dim 128)
 static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
   using L = AttnSmem<D, STAGES>;
-  using L2 = AttnV2Smem<2, 2>;
-  using L3 = AttnV3Smem<4, 4>;
   using L4 = AttnV4Smem<2, 2>;
   using L5 = AttnV5Smem<3, 3>;
-  constexpr bool V2 = (VER == 2);
-  constexpr int BKV = (VER == 2 || VER == 4) ? V2_BK : (VER == 5) ? V5_BK : ATT_BK;
+  constexpr int BKV = (VER == 4) ? V2_BK : (VER == 5) ? V5_BK : ATT_BK;
   CUtensorMap tmQ, tmK, tmV;
   const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
   const int sk_chunk = chunks > 1 ? a->sk_chunk : a->sk;
@@ -1749,27 +1079,7 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
 
   dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
   static bool attr_set = false;
-  if constexpr (V2) {
-    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
-    static const int seq = []() { const char* e = getenv("AMB_ATTN_SEQ"); return e ? atoi(e) : 0; }();
-    using KernT = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const AttnParams);
-    static const KernT table[2][6] = {
-        {flash_attn_fwd_v2_kernel<2, 2, 0, false>, flash_attn_fwd_v2_kernel<2, 2, 2, false>,
-         flash_attn_fwd_v2_kernel<2, 2, 3, false>, flash_attn_fwd_v2_kernel<2, 2, 4, false>,
-         flash_attn_fwd_v2_kernel<2, 2, 9, false>, flash_attn_fwd_v2_kernel<2, 2, 8, false>},
-        {flash_attn_fwd_v2_kernel<2, 2, 0, true>, flash_attn_fwd_v2_kernel<2, 2, 2, true>,
-         flash_attn_fwd_v2_kernel<2, 2, 3, true>, flash_attn_fwd_v2_kernel<2, 2, 4, true>,
-         flash_attn_fwd_v2_kernel<2, 2, 9, true>, flash_attn_fwd_v2_kernel<2, 2, 8, true>}};
-    const int ei = emu == 0 ? 0 : emu == 2 ? 1 : emu == 3 ? 2 : emu == 9 ? 4 : emu == 8 ? 5 : 3;
-    KernT kern = table[seq ? 1 : 0][ei];
-    if (!attr_set) {
-      for (int a_ = 0; a_ < 2; ++a_)
-        for (int b_ = 0; b_ < 6; ++b_)
-          AMB_CHECK_CUDA(cudaFuncSetAttribute(table[a_][b_], cudaFuncAttributeMaxDynamicSharedMemorySize, L2::TOTAL));
-      attr_set = true;
-    }
-    kern<<<grid, V2_THREADS, L2::TOTAL, stream>>>(tmQ, tmK, tmV, p);
-  } else if constexpr (VER == 5) {
+  if constexpr (VER == 5) {
     static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
     auto kern = emu == 0 ? flash_attn_fwd_v5_kernel<3, 3, 0>
               : emu == 2 ? flash_attn_fwd_v5_kernel<3, 3, 2>
@@ -1793,20 +1103,6 @@ static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
       attr_set = true;
     }
     kern<<<grid, V4_THREADS, L4::TOTAL, stream>>>(tmQ, tmK, tmV, p);
-  } else if constexpr (VER == 3) {
-    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
-    auto kern = emu == 0 ? flash_attn_fwd_v3_kernel<4, 4, 0>
-              : emu == 2 ? flash_attn_fwd_v3_kernel<4, 4, 2>
-              : emu == 3 ? flash_attn_fwd_v3_kernel<4, 4, 3>
-                         : flash_attn_fwd_v3_kernel<4, 4, 4>;
-    if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v3_kernel<4, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3::TOTAL));
-      attr_set = true;
-    }
-    kern<<<grid, V3_THREADS, L3::TOTAL, stream>>>(tmQ, tmK, tmV, p);
   } else {
     auto kern = flash_attn_fwd_kernel<D, STAGES>;
     if (!attr_set) {
@@ -1841,11 +1137,9 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
                 "flash_attn: kv_chunks * sk_chunk must equal sk");
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
-  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 4; }();  // v4 is the product kernel; 1-3 kept for A/B
+  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 4; }();  // 4 = product kernel; 1 and 5 kept for A/B
   if (a->head_dim == 128) {
     if (ver == 1) return launch_attn<128, 3, 1>(a, s);
-    if (ver == 2) return launch_attn<128, 3, 2>(a, s);
-    if (ver == 3) return launch_attn<128, 3, 3>(a, s);
     if (ver == 5) return launch_attn<128, 3, 5>(a, s);
     return launch_attn<128, 3, 4>(a, s);
   }

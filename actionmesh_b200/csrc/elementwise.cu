@@ -210,6 +210,61 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
   }
 }
 
+// Stage II (temporal_autoencoder.py): (source_alpha, target_alpha) token, embeddings.py:56-132 TimestepEmbedder with
+// frequency_embedding_size = size: [cos(s w) | sin(s w) | cos(t w) | sin(t w)], w_i = exp(-ln(1e4) i / (size/2)).
+// The same 2*size vector is written to n_rows rows (one alpha token per frame).
+__global__ void alpha_rows_kernel(float src, float tgt, int size, __nv_bfloat16* __restrict__ out, long long row_stride,
+                                  int n_rows) {
+  const int half = size >> 1;
+  for (int i = threadIdx.x; i < 2 * size; i += blockDim.x) {
+    const int which = i / size, j = i % size;
+    const float t = which ? tgt : src;
+    const int f = j % half;
+    const float a = t * expf(-9.210340371976184f * (float)f / (float)half);
+    const float v = (j < half) ? cosf(a) : sinf(a);
+    out[(long long)blockIdx.x * row_stride + i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Stage II query embedding, embeddings.py:15-53 FrequencyPositionalEmbedding(logspace, include_input) + extra features:
+// [x (3) | sin(x_c 2^f) (3*F) | cos(x_c 2^f) (3*F) | extra (E) | 0 ...] padded to `kpad` bf16 columns.
+__global__ void __launch_bounds__(256) point_embedding_kernel(const float* __restrict__ q, int n_points, int in_dim, int extra,
+                                                              int num_freqs, int include_pi, __nv_bfloat16* __restrict__ out,
+                                                              int kpad) {
+  const long long total = (long long)n_points * kpad;
+  const int nf3 = 3 * num_freqs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % kpad);
+    const long long pt = i / kpad;
+    const float* x = q + pt * in_dim;
+    float v = 0.f;
+    if (col < 3) {
+      v = x[col];
+    } else if (col < 3 + 2 * nf3) {
+      const int k = (col - 3) % nf3, c = k / num_freqs, f = k % num_freqs;
+      float fr = (float)(1 << f);
+      if (include_pi) fr *= 3.14159265358979323846f;
+      const float a = x[c] * fr;
+      v = (col < 3 + nf3) ? sinf(a) : cosf(a);
+    } else if (col < 3 + 2 * nf3 + extra) {
+      v = x[3 + (col - 3 - 2 * nf3)];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// Stage II output head: displacement = 2 * sigmoid(-logit) - 1 on the first `out_dim` columns (temporal_autoencoder.py:160,269)
+__global__ void __launch_bounds__(256) displacement_out_kernel(const float* __restrict__ logits, long long ld, int n_points,
+                                                               int out_dim, float* __restrict__ out) {
+  const long long total = (long long)n_points * out_dim;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long pt = i / out_dim;
+    const int c = (int)(i % out_dim);
+    const float x = -logits[pt * ld + c];
+    out[i] = 2.0f / (1.0f + expf(-x)) - 1.0f;
+  }
+}
+
 static int grid_for(long long work_items, int block) {
   long long g = (work_items + block - 1) / block;
   const long long cap = (long long)num_sms() * 16;  // grid-stride loops; a few waves of resident CTAs
@@ -292,6 +347,37 @@ int amb_patchify(const float* pixels, void* out_bf16, int n_images, int height, 
   const long long total = (long long)n_images * (height / patch) * (width / patch) * kpad;
   patchify_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(pixels, reinterpret_cast<__nv_bfloat16*>(out_bf16),
                                                                            n_images, height, width, patch, kpad);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_alpha_rows(float source_alpha, float target_alpha, int size, void* out_bf16, int64_t row_stride, int n_rows,
+                   amb_stream_t stream) {
+  AMB_CHECK_ARG(out_bf16 && size > 0 && size % 2 == 0, "alpha_rows: bad arguments");
+  if (n_rows <= 0) return AMB_OK;
+  alpha_rows_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(source_alpha, target_alpha, size,
+                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), row_stride, n_rows);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_point_embedding(const float* points, int n_points, int in_dim, int extra, int num_freqs, int include_pi,
+                        void* out_bf16, int kpad, amb_stream_t stream) {
+  AMB_CHECK_ARG(points && out_bf16, "point_embedding: null pointer");
+  AMB_CHECK_ARG(in_dim == 3 + extra && kpad % 64 == 0 && kpad >= 3 + 6 * num_freqs + extra && num_freqs >= 0 && num_freqs < 24,
+                "point_embedding: bad geometry in_dim=%d extra=%d freqs=%d kpad=%d", in_dim, extra, num_freqs, kpad);
+  if (n_points <= 0) return AMB_OK;
+  point_embedding_kernel<<<grid_for((long long)n_points * kpad, 256), 256, 0, (cudaStream_t)stream>>>(
+      points, n_points, in_dim, extra, num_freqs, include_pi, reinterpret_cast<__nv_bfloat16*>(out_bf16), kpad);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_displacement_out(const float* logits, int64_t ld, int n_points, int out_dim, float* out, amb_stream_t stream) {
+  AMB_CHECK_ARG(logits && out && out_dim > 0 && ld >= out_dim, "displacement_out: bad arguments");
+  if (n_points <= 0) return AMB_OK;
+  displacement_out_kernel<<<grid_for((long long)n_points * out_dim, 256), 256, 0, (cudaStream_t)stream>>>(logits, ld, n_points,
+                                                                                                        out_dim, out);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -117,8 +117,8 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int n0, int row, long long drow,
                                               bool valid) {
-  if (n0 < p.norm_cols) {
-    // ---- per-head RMSNorm (+ RoPE): one head = 128 accumulator columns, all owned by this thread ----
+  if (n0 < (p.norm_cols > p.rope_cols ? p.norm_cols : p.rope_cols)) {
+    // ---- per-head RMSNorm and/or RoPE: one head = 128 accumulator columns, all owned by this thread ----
     if constexpr (BN % 128 == 0) {
 #pragma unroll 1
       for (int hc = 0; hc < BN; hc += 128) {
@@ -127,16 +127,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld_x32f(taddr + hc + c * 32, v + c * 32);
         tmem_wait_ld();
-        if (col0 < p.norm_cols) {
-          float ss = 0.f;
+        if (col0 < p.norm_cols || col0 < p.rope_cols) {
+          if (col0 < p.norm_cols) {
+            float ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
-          const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
-          const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
+            for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
+            const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+            const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
 #pragma unroll
-          for (int j = 0; j < 128; j += 4) {
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
-            v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
+            for (int j = 0; j < 128; j += 4) {
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
+              v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
+            }
           }
           if (col0 < p.rope_cols) {
             const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
@@ -582,10 +584,10 @@ extern "C" int amb_gemm_bf16(const amb_gemm_args* a, amb_stream_t stream) {
                 "gemm: bad k_split %d", a->k_split);
   AMB_CHECK_ARG(!a->residual || a->ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
   AMB_CHECK_ARG(a->act == 0 || a->act == 1, "gemm: unknown activation %d", a->act);
-  if (a->norm_cols > 0) {
-    AMB_CHECK_ARG(a->n % 128 == 0 && a->norm_cols % 128 == 0 && a->norm_w0, "gemm: head epilogue needs n %% 128 == 0 and norm weights");
-    AMB_CHECK_ARG(a->norm_seg % 128 == 0, "gemm: norm_seg must be a multiple of 128");
-    AMB_CHECK_ARG(a->rope_cols % 128 == 0 && a->rope_cols <= a->norm_cols, "gemm: rope_cols must be a multiple of 128 and <= norm_cols");
+  if (a->norm_cols > 0 || a->rope_cols > 0) {
+    AMB_CHECK_ARG(a->n % 128 == 0 && a->norm_cols % 128 == 0 && a->rope_cols % 128 == 0,
+                  "gemm: head epilogue needs n, norm_cols, rope_cols multiples of 128");
+    AMB_CHECK_ARG(a->norm_cols == 0 || (a->norm_w0 && a->norm_seg % 128 == 0), "gemm: norm weights / norm_seg (multiple of 128) required");
     AMB_CHECK_ARG(a->rope_cols == 0 || (a->rope_cos && a->rope_sin), "gemm: rope tables required");
     AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale, "gemm: head epilogue excludes residual/activation/col_scale");
   }

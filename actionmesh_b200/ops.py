@@ -108,6 +108,43 @@ def patchify(pixels: torch.Tensor, patch: int, kpad: int, out: Optional[torch.Te
     return out
 
 
+def alpha_rows(source_alpha: float, target_alpha: float, size: int, out_rows: torch.Tensor) -> None:
+    """Write the (source, target) alpha token (2*size bf16 values) into every row of the strided 2-D view `out_rows`."""
+    global launch_count
+    _need(out_rows, torch.bfloat16, "out_rows")
+    assert out_rows.dim() == 2 and out_rows.shape[1] == 2 * size and out_rows.stride(1) == 1
+    rc = _lib.load_library().amb_alpha_rows(float(source_alpha), float(target_alpha), size, out_rows.data_ptr(),
+                                            out_rows.stride(0), out_rows.shape[0], _stream())
+    _lib.check(rc, "amb_alpha_rows")
+    launch_count += 1
+
+
+def point_embedding(points: torch.Tensor, num_freqs: int, include_pi: bool, kpad: int) -> torch.Tensor:
+    """(V, 3+E) fp32 query points -> (V, kpad) bf16 [x | sin | cos | extra | 0-pad] rows."""
+    global launch_count
+    _need(points, torch.float32, "points")
+    assert points.dim() == 2 and points.is_contiguous()
+    V, in_dim = points.shape
+    out = torch.empty(V, kpad, dtype=torch.bfloat16, device=points.device)
+    rc = _lib.load_library().amb_point_embedding(points.data_ptr(), V, in_dim, in_dim - 3, num_freqs, int(include_pi),
+                                                 out.data_ptr(), kpad, _stream())
+    _lib.check(rc, "amb_point_embedding")
+    launch_count += 1
+    return out
+
+
+def displacement_out(logits: torch.Tensor, out_dim: int, out: torch.Tensor) -> torch.Tensor:
+    global launch_count
+    _need(logits, torch.float32, "logits")
+    _need(out, torch.float32, "out")
+    assert logits.dim() == 2 and logits.stride(1) == 1 and out.is_contiguous()
+    rc = _lib.load_library().amb_displacement_out(logits.data_ptr(), logits.stride(0), logits.shape[0], out_dim,
+                                                  out.data_ptr(), _stream())
+    _lib.check(rc, "amb_displacement_out")
+    launch_count += 1
+    return out
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global launch_count
     _need(src, torch.float32, "src")
@@ -194,10 +231,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     else:
         g.grp_rows = g.grp_stride = g.row_off = 0
     if norm is not None:
-        g.norm_cols, g.norm_seg = norm["cols"], norm.get("seg", norm["cols"])
-        g.norm_w0 = norm["w0"].data_ptr()
+        g.norm_cols, g.norm_seg = norm.get("cols", 0), norm.get("seg", norm.get("cols", 0))
+        g.norm_w0 = norm["w0"].data_ptr() if norm.get("w0") is not None else None
         g.norm_w1 = norm["w1"].data_ptr() if norm.get("w1") is not None else None
-        g.norm_eps = float(norm["eps"])
+        g.norm_eps = float(norm.get("eps", 0.0))
         g.rope_cols = norm.get("rope_cols", 0)
         g.rope_cos = _ptr(norm.get("cos"))
         g.rope_sin = _ptr(norm.get("sin"))

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 6
+#define AMB_ABI_VERSION 7
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -69,6 +69,18 @@ int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows,
                            amb_stream_t stream);
 int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream);
 
+/* ---- Stage II (temporal autoencoder) helpers — first "next" row of SURVEY 8(f) -----------------------------------------
+ * alpha_rows: the (source_alpha, target_alpha) token of actionmesh/model/temporal_autoencoder.py:233-237 (TimestepEmbedder,
+ *   model/utils/embeddings.py:56-132), written to n_rows rows `row_stride` elements apart.
+ * point_embedding: FrequencyPositionalEmbedding of the query vertices (+ normals), temporal_autoencoder.py:240-243,
+ *   embeddings.py:15-53, as bf16 rows padded to kpad columns for the proj_query GEMM.
+ * displacement_out: 2*sigmoid(-logits) - 1 on the first out_dim columns (temporal_autoencoder.py:160,269). */
+int amb_alpha_rows(float source_alpha, float target_alpha, int size, void* out_bf16, int64_t row_stride, int n_rows,
+                   amb_stream_t stream);
+int amb_point_embedding(const float* points, int n_points, int in_dim, int extra, int num_freqs, int include_pi,
+                        void* out_bf16, int kpad, amb_stream_t stream);
+int amb_displacement_out(const float* logits, int64_t ld, int n_points, int out_dim, float* out, amb_stream_t stream);
+
 /* ---- tcgen05 GEMM with fused epilogues: C = epi(A · Wᵀ) ----------------------------------------------------------------
  * Replaces every nn.Linear on the path (cuBLAS in the reference): proj_in/proj_out/time_proj
  * (temporal_denoiser.py:206,213-214,242), linear_skip on cat[skip,h] without materialising the concat (block.py:131-133,
@@ -97,7 +109,8 @@ typedef struct amb_gemm_args {
   const float* col_scale; /* (n) or NULL: per-column scale applied after bias/act, before residual (DinoV2 LayerScale) */
   /* output row remap: dst_row = (row / grp_rows) * grp_stride + row % grp_rows + row_off  (grp_rows == 0: identity) */
   int32_t grp_rows, grp_stride, row_off;
-  /* per-head (128 columns) RMSNorm for columns [0, norm_cols): weight norm_w0 for col < norm_seg, norm_w1 otherwise */
+  /* per-head (128 columns) RMSNorm for columns [0, norm_cols): weight norm_w0 for col < norm_seg, norm_w1 otherwise
+   * (norm_cols may be 0 with rope_cols > 0: RoPE without q/k norm, as in the Stage-II blocks) */
   int32_t norm_cols, norm_seg;
   const float* norm_w0;
   const float* norm_w1;
