@@ -213,8 +213,7 @@ __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__
 // Stage II (temporal_autoencoder.py): (source_alpha, target_alpha) token, embeddings.py:56-132 TimestepEmbedder with
 // frequency_embedding_size = size: [cos(s w) | sin(s w) | cos(t w) | sin(t w)], w_i = exp(-ln(1e4) i / (size/2)).
 // The same 2*size vector is written to n_rows rows (one alpha token per frame).
-__global__ void alpha_rows_kernel(float src, float tgt, int size, __nv_bfloat16* __restrict__ out, long long row_stride,
-                                  int n_rows) {
+__global__ void alpha_rows_kernel(float src, float tgt, int size, float* __restrict__ out, long long row_stride, int n_rows) {
   const int half = size >> 1;
   for (int i = threadIdx.x; i < 2 * size; i += blockDim.x) {
     const int which = i / size, j = i % size;
@@ -222,15 +221,15 @@ __global__ void alpha_rows_kernel(float src, float tgt, int size, __nv_bfloat16*
     const int f = j % half;
     const float a = t * expf(-9.210340371976184f * (float)f / (float)half);
     const float v = (j < half) ? cosf(a) : sinf(a);
-    out[(long long)blockIdx.x * row_stride + i] = __float2bfloat16_rn(v);
+    out[(long long)blockIdx.x * row_stride + i] = v;
   }
 }
 
 // Stage II query embedding, embeddings.py:15-53 FrequencyPositionalEmbedding(logspace, include_input) + extra features:
-// [x (3) | sin(x_c 2^f) (3*F) | cos(x_c 2^f) (3*F) | extra (E) | 0 ...] padded to `kpad` bf16 columns.
+// [x (3) | sin(x_c 2^f) (3*F) | cos(x_c 2^f) (3*F) | extra (E) | 0 ...] padded to `kpad` fp32 columns (the reference keeps
+// the whole query path in fp32, temporal_autoencoder.py:240-243,264-266).
 __global__ void __launch_bounds__(256) point_embedding_kernel(const float* __restrict__ q, int n_points, int in_dim, int extra,
-                                                              int num_freqs, int include_pi, __nv_bfloat16* __restrict__ out,
-                                                              int kpad) {
+                                                              int num_freqs, int include_pi, float* __restrict__ out, int kpad) {
   const long long total = (long long)n_points * kpad;
   const int nf3 = 3 * num_freqs;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -249,7 +248,88 @@ __global__ void __launch_bounds__(256) point_embedding_kernel(const float* __res
     } else if (col < 3 + 2 * nf3 + extra) {
       v = x[3 + (col - 3 - 2 * nf3)];
     }
-    out[i] = __float2bfloat16_rn(v);
+    out[i] = v;
+  }
+}
+
+// ---- split-bf16 ("3x bf16") operands for the fp32-grade GEMMs of the Stage-II query path ------------------------------
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi) (|x - hi - lo| <= 2^-17 |x|).  A product a*w is evaluated on the tensor
+// cores as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo by concatenating along K: A-pattern [hi | lo | hi], W-pattern [hi | hi | lo].
+// The source is cut in segments of `seg` columns; each becomes 3*seg destination columns (seg = cols for a plain GEMM
+// operand, seg = head_dim for per-head attention operands).
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ src, long long ld_src, long long rows, int cols,
+                                                     int seg, int w_pattern, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  const int c4 = cols >> 2;
+  const long long total = rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int c = (int)(i % c4) << 2;
+    const float4 x = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hi[j] = __float2bfloat16_rn(xs[j]);
+      lo[j] = __float2bfloat16_rn(xs[j] - __bfloat162float(hi[j]));
+    }
+    const int s = c / seg, j0 = c % seg;
+    __nv_bfloat16* d = dst + r * ld_dst + (long long)s * 3 * seg + j0;
+    const uint2 vh = *reinterpret_cast<const uint2*>(hi), vl = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(d) = vh;
+    *reinterpret_cast<uint2*>(d + seg) = w_pattern ? vh : vl;
+    *reinterpret_cast<uint2*>(d + 2 * seg) = w_pattern ? vl : vh;
+  }
+}
+
+// Row softmax of fp32 scores (one CTA per row, the row staged in shared memory), written as the A-pattern split
+// [P_hi | P_lo | P_hi] with each part n_pad wide and zeros in the padding columns [n, n_pad).
+__global__ void __launch_bounds__(512) softmax_split3_kernel(const float* __restrict__ s, long long ld_s, int n, int n_pad,
+                                                             float scale, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  extern __shared__ float row[];
+  __shared__ float red[16];
+  const float* src = s + (long long)blockIdx.x * ld_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float mx = -INFINITY;
+  for (int c = tid * 4; c < n; c += blockDim.x * 4) {  // n % 4 == 0
+    float4 x = *reinterpret_cast<const float4*>(src + c);
+    x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+    *reinterpret_cast<float4*>(row + c) = x;
+    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int c = tid * 4; c < n; c += blockDim.x * 4) {
+    float4 x = *reinterpret_cast<const float4*>(row + c);
+    x.x = expf(x.x - mx); x.y = expf(x.y - mx); x.z = expf(x.z - mx); x.w = expf(x.w - mx);
+    *reinterpret_cast<float4*>(row + c) = x;
+    sum += (x.x + x.y) + (x.z + x.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+  __nv_bfloat16* d = dst + (long long)blockIdx.x * ld_dst;
+  for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float p = (c + j < n) ? row[c + j] * inv : 0.f;
+      hi[j] = __float2bfloat16_rn(p);
+      lo[j] = __float2bfloat16_rn(p - __bfloat162float(hi[j]));
+    }
+    const uint2 vh = *reinterpret_cast<const uint2*>(hi), vl = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(d + c) = vh;
+    *reinterpret_cast<uint2*>(d + n_pad + c) = vl;
+    *reinterpret_cast<uint2*>(d + 2 * n_pad + c) = vh;
   }
 }
 
@@ -351,24 +431,55 @@ int amb_patchify(const float* pixels, void* out_bf16, int n_images, int height, 
   return AMB_OK;
 }
 
-int amb_alpha_rows(float source_alpha, float target_alpha, int size, void* out_bf16, int64_t row_stride, int n_rows,
+int amb_alpha_rows(float source_alpha, float target_alpha, int size, float* out, int64_t row_stride, int n_rows,
                    amb_stream_t stream) {
-  AMB_CHECK_ARG(out_bf16 && size > 0 && size % 2 == 0, "alpha_rows: bad arguments");
+  AMB_CHECK_ARG(out && size > 0 && size % 2 == 0, "alpha_rows: bad arguments");
   if (n_rows <= 0) return AMB_OK;
-  alpha_rows_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(source_alpha, target_alpha, size,
-                                                            reinterpret_cast<__nv_bfloat16*>(out_bf16), row_stride, n_rows);
+  alpha_rows_kernel<<<n_rows, 256, 0, (cudaStream_t)stream>>>(source_alpha, target_alpha, size, out, row_stride, n_rows);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_split3_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, int seg, int w_pattern, void* dst_bf16,
+                    int64_t ld_dst, amb_stream_t stream) {
+  AMB_CHECK_ARG(src && dst_bf16, "split3: null pointer");
+  AMB_CHECK_ARG(cols > 0 && seg > 0 && cols % seg == 0 && seg % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 &&
+                    ld_dst >= 3LL * cols && ld_src >= cols,
+                "split3: bad geometry cols=%d seg=%d ld_src=%lld ld_dst=%lld", cols, seg, (long long)ld_src, (long long)ld_dst);
+  if (rows <= 0) return AMB_OK;
+  split3_kernel<<<grid_for(rows * (cols / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      src, ld_src, rows, cols, seg, w_pattern, reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_softmax_split3(const float* scores, int64_t ld_s, int rows, int n, int n_pad, float scale, void* dst_bf16,
+                       int64_t ld_dst, amb_stream_t stream) {
+  AMB_CHECK_ARG(scores && dst_bf16, "softmax_split3: null pointer");
+  AMB_CHECK_ARG(n > 0 && n % 4 == 0 && n_pad >= n && n_pad % 4 == 0 && ld_s % 4 == 0 && ld_dst % 4 == 0 && ld_dst >= 3LL * n_pad,
+                "softmax_split3: bad geometry n=%d n_pad=%d", n, n_pad);
+  const size_t smem = (size_t)n * sizeof(float);
+  AMB_CHECK_ARG(smem <= 200 * 1024, "softmax_split3: row of %d scores does not fit shared memory", n);
+  if (rows <= 0) return AMB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    AMB_CHECK_CUDA(cudaFuncSetAttribute(softmax_split3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  softmax_split3_kernel<<<rows, 512, smem, (cudaStream_t)stream>>>(scores, ld_s, n, n_pad, scale,
+                                                                  reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }
 
 int amb_point_embedding(const float* points, int n_points, int in_dim, int extra, int num_freqs, int include_pi,
-                        void* out_bf16, int kpad, amb_stream_t stream) {
-  AMB_CHECK_ARG(points && out_bf16, "point_embedding: null pointer");
+                        float* out, int kpad, amb_stream_t stream) {
+  AMB_CHECK_ARG(points && out, "point_embedding: null pointer");
   AMB_CHECK_ARG(in_dim == 3 + extra && kpad % 64 == 0 && kpad >= 3 + 6 * num_freqs + extra && num_freqs >= 0 && num_freqs < 24,
                 "point_embedding: bad geometry in_dim=%d extra=%d freqs=%d kpad=%d", in_dim, extra, num_freqs, kpad);
   if (n_points <= 0) return AMB_OK;
   point_embedding_kernel<<<grid_for((long long)n_points * kpad, 256), 256, 0, (cudaStream_t)stream>>>(
-      points, n_points, in_dim, extra, num_freqs, include_pi, reinterpret_cast<__nv_bfloat16*>(out_bf16), kpad);
+      points, n_points, in_dim, extra, num_freqs, include_pi, out, kpad);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -109,9 +109,9 @@ def patchify(pixels: torch.Tensor, patch: int, kpad: int, out: Optional[torch.Te
 
 
 def alpha_rows(source_alpha: float, target_alpha: float, size: int, out_rows: torch.Tensor) -> None:
-    """Write the (source, target) alpha token (2*size bf16 values) into every row of the strided 2-D view `out_rows`."""
+    """Write the (source, target) alpha token (2*size fp32 values) into every row of the strided 2-D view `out_rows`."""
     global launch_count
-    _need(out_rows, torch.bfloat16, "out_rows")
+    _need(out_rows, torch.float32, "out_rows")
     assert out_rows.dim() == 2 and out_rows.shape[1] == 2 * size and out_rows.stride(1) == 1
     rc = _lib.load_library().amb_alpha_rows(float(source_alpha), float(target_alpha), size, out_rows.data_ptr(),
                                             out_rows.stride(0), out_rows.shape[0], _stream())
@@ -120,15 +120,44 @@ def alpha_rows(source_alpha: float, target_alpha: float, size: int, out_rows: to
 
 
 def point_embedding(points: torch.Tensor, num_freqs: int, include_pi: bool, kpad: int) -> torch.Tensor:
-    """(V, 3+E) fp32 query points -> (V, kpad) bf16 [x | sin | cos | extra | 0-pad] rows."""
+    """(V, 3+E) fp32 query points -> (V, kpad) fp32 [x | sin | cos | extra | 0-pad] rows."""
     global launch_count
     _need(points, torch.float32, "points")
     assert points.dim() == 2 and points.is_contiguous()
     V, in_dim = points.shape
-    out = torch.empty(V, kpad, dtype=torch.bfloat16, device=points.device)
+    out = torch.empty(V, kpad, dtype=torch.float32, device=points.device)
     rc = _lib.load_library().amb_point_embedding(points.data_ptr(), V, in_dim, in_dim - 3, num_freqs, int(include_pi),
                                                  out.data_ptr(), kpad, _stream())
     _lib.check(rc, "amb_point_embedding")
+    launch_count += 1
+    return out
+
+
+def split3(src: torch.Tensor, out: torch.Tensor, seg: Optional[int] = None, weight: bool = False) -> torch.Tensor:
+    """fp32 (rows, cols) -> bf16 (rows, 3*cols) split operand: [hi|lo|hi] per segment (activations) or [hi|hi|lo] (weights)."""
+    global launch_count
+    _need(src, torch.float32, "src")
+    _need(out, torch.bfloat16, "out")
+    assert src.dim() == 2 and out.dim() == 2 and src.stride(1) == 1 and out.stride(1) == 1
+    rows, cols = src.shape
+    assert out.shape[0] >= rows and out.shape[1] == 3 * cols
+    rc = _lib.load_library().amb_split3_bf16(src.data_ptr(), src.stride(0), rows, cols, seg or cols, int(weight),
+                                             out.data_ptr(), out.stride(0), _stream())
+    _lib.check(rc, "amb_split3_bf16")
+    launch_count += 1
+    return out
+
+
+def softmax_split3(scores: torch.Tensor, n: int, scale: float, out: torch.Tensor) -> torch.Tensor:
+    """Row softmax over the first n columns of fp32 `scores` (rows, n_pad), written as [P_hi|P_lo|P_hi] (rows, 3*n_pad)."""
+    global launch_count
+    _need(scores, torch.float32, "scores")
+    _need(out, torch.bfloat16, "out")
+    rows, n_pad = scores.shape
+    assert scores.stride(1) == 1 and out.stride(1) == 1 and out.shape == (rows, 3 * n_pad)
+    rc = _lib.load_library().amb_softmax_split3(scores.data_ptr(), scores.stride(0), rows, n, n_pad, float(scale),
+                                                out.data_ptr(), out.stride(0), _stream())
+    _lib.check(rc, "amb_softmax_split3")
     launch_count += 1
     return out
 

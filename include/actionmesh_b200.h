@@ -71,15 +71,26 @@ int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows
 
 /* ---- Stage II (temporal autoencoder) helpers — first "next" row of SURVEY 8(f) -----------------------------------------
  * alpha_rows: the (source_alpha, target_alpha) token of actionmesh/model/temporal_autoencoder.py:233-237 (TimestepEmbedder,
- *   model/utils/embeddings.py:56-132), written to n_rows rows `row_stride` elements apart.
+ *   model/utils/embeddings.py:56-132), fp32, written to n_rows rows `row_stride` elements apart.
  * point_embedding: FrequencyPositionalEmbedding of the query vertices (+ normals), temporal_autoencoder.py:240-243,
- *   embeddings.py:15-53, as bf16 rows padded to kpad columns for the proj_query GEMM.
- * displacement_out: 2*sigmoid(-logits) - 1 on the first out_dim columns (temporal_autoencoder.py:160,269). */
-int amb_alpha_rows(float source_alpha, float target_alpha, int size, void* out_bf16, int64_t row_stride, int n_rows,
+ *   embeddings.py:15-53, as fp32 rows zero-padded to kpad columns for the proj_query GEMM.
+ * displacement_out: 2*sigmoid(-logits) - 1 on the first out_dim columns (temporal_autoencoder.py:160,269).
+ * split3_bf16 / softmax_split3: the reference runs the vertex-query cross-attention block with autocast DISABLED (fp32,
+ *   temporal_autoencoder.py:264-266).  Here that block runs on the bf16 tensor cores at fp32-grade accuracy by splitting
+ *   every operand x = hi + lo (two bf16) and concatenating along K: activations as [hi | lo | hi] (w_pattern = 0),
+ *   weights as [hi | hi | lo] (w_pattern = 1), so one amb_gemm_bf16 call evaluates a_hi w_hi + a_lo w_hi + a_hi w_lo
+ *   with fp32 accumulation.  split3_bf16 cuts `cols` in segments of `seg` columns (each becomes 3*seg output columns);
+ *   softmax_split3 does the row softmax of fp32 scores (n valid columns, scaled by `scale`) and writes the probabilities
+ *   as the activation split with each part n_pad wide (zeros in the padding). */
+int amb_alpha_rows(float source_alpha, float target_alpha, int size, float* out, int64_t row_stride, int n_rows,
                    amb_stream_t stream);
 int amb_point_embedding(const float* points, int n_points, int in_dim, int extra, int num_freqs, int include_pi,
-                        void* out_bf16, int kpad, amb_stream_t stream);
+                        float* out, int kpad, amb_stream_t stream);
 int amb_displacement_out(const float* logits, int64_t ld, int n_points, int out_dim, float* out, amb_stream_t stream);
+int amb_split3_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, int seg, int w_pattern, void* dst_bf16,
+                    int64_t ld_dst, amb_stream_t stream);
+int amb_softmax_split3(const float* scores, int64_t ld_s, int rows, int n, int n_pad, float scale, void* dst_bf16,
+                       int64_t ld_dst, amb_stream_t stream);
 
 /* ---- tcgen05 GEMM with fused epilogues: C = epi(A · Wᵀ) ----------------------------------------------------------------
  * Replaces every nn.Linear on the path (cuBLAS in the reference): proj_in/proj_out/time_proj

@@ -95,6 +95,7 @@ def test_gemm_is_linear_in_a(probe):
     ("sharp_rescale", (1, 2, 512, 1024, 128), dict(mode="sharp")),
     ("fused_qkv_strided", (2, 4, 520, 520, 128), dict(fused=True)),
     ("kv_chunks2", (2, 2, 256, 400, 128), dict(kv_chunks=2)),
+    ("kv_chunks8_rank_of_8", (1, 2, 2 * 2049, 8 * 2 * 2049, 128), dict(kv_chunks=8)),   # 8-GPU frame-sharded window
     ("d64_s257", (3, 4, 257, 257, 64), {}),
     ("d64_fused", (2, 16, 257, 257, 64), dict(fused=True)),
     ("window_t2", (2, 16, 2 * 2049, 2 * 2049, 128), dict(fused=True)),
