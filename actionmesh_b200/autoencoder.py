@@ -173,6 +173,43 @@ class B200Autoencoder:
         self._w = w
         self._loaded = True
 
+    def init_random_(self, seed: int = 1236) -> None:
+        """Synthetic weights for benchmarks (no checkpoints offline): torch default Linear/LayerNorm inits, residual-branch
+        output projections scaled by 1/sqrt(num_layers + 1), generated on the GPU."""
+        c = self.config
+        dev = self._device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        rs = 1.0 / math.sqrt(c.num_layers + 1)
+        D = c.width
+
+        def lin(out_f, in_f, scale=1.0, bias=True):
+            bound = 1.0 / math.sqrt(in_f)
+            wt = (torch.rand(out_f, in_f, generator=g, device=dev) * 2 - 1) * bound * scale
+            bs = (torch.rand(out_f, generator=g, device=dev) * 2 - 1) * bound * scale if bias else None
+            return wt, bs
+
+        def ln(name):
+            sd[name + ".weight"], sd[name + ".bias"] = torch.ones(D, device=dev), torch.zeros(D, device=dev)
+
+        sd = {}
+        sd["post_quant.weight"], sd["post_quant.bias"] = lin(D, c.latent_channels)
+        sd["proj_query.weight"], sd["proj_query.bias"] = lin(D, c.query_dim)
+        sd["proj_out.weight"], sd["proj_out.bias"] = lin(c.out_dim, D)
+        ln("norm_out")
+        for i in range(c.num_layers + 1):
+            p = f"blocks.{i}."
+            a = "x_attn" if i == c.num_layers else "s_attn"
+            ln(p + ("norm_x_attn" if i == c.num_layers else "norm_s_attn"))
+            ln(p + "norm_ff")
+            if i == c.num_layers:
+                ln(p + "x_attn.norm_cross")
+            for n in ("to_q", "to_k", "to_v"):
+                sd[p + f"{a}.{n}.weight"], _ = lin(D, D, bias=False)
+            sd[p + f"{a}.to_out.0.weight"], sd[p + f"{a}.to_out.0.bias"] = lin(D, D, scale=rs)
+            sd[p + "ff.net.0.proj.weight"], sd[p + "ff.net.0.proj.bias"] = lin(4 * D, D)
+            sd[p + "ff.net.2.weight"], sd[p + "ff.net.2.bias"] = lin(D, 4 * D, scale=rs)
+        self.load_state_dict(sd)
+
     # ------------------------------------------------------------------ reference helper (temporal_autoencoder.py:118-141)
     def apply_displacement(self, vertex: torch.Tensor, displacement: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         if self.prediction_mode == "direct":
@@ -202,8 +239,6 @@ class B200Autoencoder:
         L = N + 1
         R = T * L                      # tokens of the trunk sequence == keys of the query cross-attention
         Rp = _pad64(R)
-        if R % 4:
-            raise AmbError("T*(N+1) must be a multiple of 4")
         scale = 1.0 / math.sqrt(dh)
         src_a = source_alpha.detach().to("cpu", torch.float32).tolist()
         tgt_a = target_alphas.detach().to("cpu", torch.float32).tolist()

@@ -290,9 +290,12 @@ __global__ void __launch_bounds__(512) softmax_split3_kernel(const float* __rest
   const float* src = s + (long long)blockIdx.x * ld_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float mx = -INFINITY;
-  for (int c = tid * 4; c < n; c += blockDim.x * 4) {  // n % 4 == 0
+  for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {  // columns >= n (padding / ragged tail) are masked to -inf
     float4 x = *reinterpret_cast<const float4*>(src + c);
-    x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+    x.x = (c + 0 < n) ? x.x * scale : -INFINITY;
+    x.y = (c + 1 < n) ? x.y * scale : -INFINITY;
+    x.z = (c + 2 < n) ? x.z * scale : -INFINITY;
+    x.w = (c + 3 < n) ? x.w * scale : -INFINITY;
     *reinterpret_cast<float4*>(row + c) = x;
     mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
   }
@@ -304,9 +307,9 @@ __global__ void __launch_bounds__(512) softmax_split3_kernel(const float* __rest
   for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int c = tid * 4; c < n; c += blockDim.x * 4) {
+  for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {
     float4 x = *reinterpret_cast<const float4*>(row + c);
-    x.x = expf(x.x - mx); x.y = expf(x.y - mx); x.z = expf(x.z - mx); x.w = expf(x.w - mx);
+    x.x = expf(x.x - mx); x.y = expf(x.y - mx); x.z = expf(x.z - mx); x.w = expf(x.w - mx);  // exp(-inf) == 0
     *reinterpret_cast<float4*>(row + c) = x;
     sum += (x.x + x.y) + (x.z + x.w);
   }
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(512) softmax_split3_kernel(const float* __rest
     __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float p = (c + j < n) ? row[c + j] * inv : 0.f;
+      const float p = row[c + j] * inv;
       hi[j] = __float2bfloat16_rn(p);
       lo[j] = __float2bfloat16_rn(p - __bfloat162float(hi[j]));
     }
@@ -456,9 +459,9 @@ int amb_split3_bf16(const float* src, int64_t ld_src, int64_t rows, int cols, in
 int amb_softmax_split3(const float* scores, int64_t ld_s, int rows, int n, int n_pad, float scale, void* dst_bf16,
                        int64_t ld_dst, amb_stream_t stream) {
   AMB_CHECK_ARG(scores && dst_bf16, "softmax_split3: null pointer");
-  AMB_CHECK_ARG(n > 0 && n % 4 == 0 && n_pad >= n && n_pad % 4 == 0 && ld_s % 4 == 0 && ld_dst % 4 == 0 && ld_dst >= 3LL * n_pad,
+  AMB_CHECK_ARG(n > 0 && n_pad >= n && n_pad % 4 == 0 && ld_s % 4 == 0 && ld_s >= n_pad && ld_dst % 4 == 0 && ld_dst >= 3LL * n_pad,
                 "softmax_split3: bad geometry n=%d n_pad=%d", n, n_pad);
-  const size_t smem = (size_t)n * sizeof(float);
+  const size_t smem = (size_t)n_pad * sizeof(float);
   AMB_CHECK_ARG(smem <= 200 * 1024, "softmax_split3: row of %d scores does not fit shared memory", n);
   if (rows <= 0) return AMB_OK;
   static bool attr_set = false;

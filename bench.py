@@ -313,8 +313,37 @@ def run_b200(args):
         video = {"sec_per_video_stage1": t2 - t0, "dinov2_encode_s": t1 - t0, "denoise_30_steps_s": t2 - t1,
                  "frames": T, "steps": 30, "finite": bool(torch.isfinite(lat_host).all()),
                  "note": "Stage-I path only (DinoV2 encode incl. host BitImageProcessor + 1 window x 30 steps, CFG 7.5) through "
-                         "Stage1Pipeline; Stage 0 (TripoSG) and Stage II are out of scope and not included"}
+                         "Stage1Pipeline; Stage 0 (TripoSG) is out of scope and not included; Stage II is timed separately below"}
         del enc, pipe
+        # Stage II on the same window: 16-block trunk re-run for each of the 15 target times + the
+        # fp32-grade vertex-query block for V = 20 000 anchor vertices (+ normals), B200Autoencoder.forward, host in/out.
+        from actionmesh_b200.autoencoder import B200Autoencoder
+
+        ae = B200Autoencoder().to(dev)
+        ae.init_random_(seed=1236)
+        gq = torch.Generator().manual_seed(13)
+        pts = torch.randn(1, 20000, 3, generator=gq)
+        pts = pts / pts.norm(dim=-1, keepdim=True) * 0.6
+        query = torch.cat([pts, pts / 0.6], dim=-1)
+        tgt = torch.linspace(0, 1, T)[None, 1:]
+        ae.forward(lat_host[None, :3], torch.arange(3.0)[None], torch.zeros(1), tgt[:, :1], query[:, :512])  # warm-up
+        ops.event_log, ops.event_tags = [], {"s2_attn", "s2_gemm", "s2_q"}
+        torch.cuda.synchronize()
+        t3 = time.perf_counter()
+        disp = ae.forward(lat_host[None], torch.arange(T, dtype=torch.float32)[None], torch.zeros(1), tgt, query)
+        verts = ae.apply_displacement(query[..., :3].to(dev), disp).cpu()
+        torch.cuda.synchronize()
+        t4 = time.perf_counter()
+        s2 = {}
+        for tag, e0, e1 in ops.event_log:
+            s2[tag] = s2.get(tag, 0.0) + e0.elapsed_time(e1)
+        ops.event_log = None
+        video.update({"stage2_decode_s": t4 - t3, "stage2_targets": int(tgt.shape[1]), "stage2_vertices": 20000,
+                      "stage2_kernel_ms": {"trunk_attention": s2.get("s2_attn"), "trunk_gemm": s2.get("s2_gemm"),
+                                           "query_path_gemm": s2.get("s2_q")},
+                      "stage2_finite": bool(torch.isfinite(verts).all()),
+                      "sec_per_video_stage1_plus_stage2": (t2 - t0) + (t4 - t3)})
+        del ae
 
     if rank != 0:
         if world > 1:

@@ -74,8 +74,8 @@ def test_query_path_is_fp32_grade(amb_lib):
     cfg = ao.AutoencoderConfig(width=256, num_layers=0, num_attention_heads=2)
     sd = ao.make_autoencoder_state_dict(cfg, 77)
     gen = torch.Generator().manual_seed(5)
-    lat = torch.randn(1, 4, 31, 64, generator=gen).bfloat16().float()  # bf16-representable: post_quant is then exact
-    fs = torch.tensor([[5.0, 6.0, 7.0, 9.0]])
+    lat = torch.randn(1, 3, 30, 64, generator=gen).bfloat16().float()  # bf16-representable: post_quant is then exact
+    fs = torch.tensor([[5.0, 6.0, 9.0]])  # R = 3 * 31 = 93 keys: odd, exercises the padded / masked softmax tail
     sa, ta = torch.tensor([0.25]), torch.tensor([[0.0, 0.6]])
     q = torch.rand(1, 700, 6, generator=gen) * 2 - 1
     m = _model(cfg, sd)
