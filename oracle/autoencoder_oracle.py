@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — fp32 CPU restatement of the reference's Stage-II temporal autoencoder and of the ActionBench
-Chamfer metric, used to turn Stage-I latents into per-frame vertices so that parity can be reported as the Chamfer
-distance `north_star` names (Stage II itself is out of scope for the CUDA path this round: both the B200 latents and the
-oracle latents are decoded by THIS same fp32 decoder).
+Chamfer metric: (1) the checker of the CUDA Stage-II path (actionmesh_b200/autoencoder.py, tests/test_autoencoder_gpu.py),
+(2) the common fp32 decoder that turns Stage-I latents of both paths into per-frame vertices so that Stage-I parity can be
+reported as the Chamfer distance `north_star` names (tests/test_chamfer_gpu.py).
 
   autoencoder_forward : actionmesh/model/temporal_autoencoder.py:163-269 (ActionMeshAutoencoder.forward)
   chamfer_score       : actionbench/chamfer.py:12-50 (compute_chamfer_score; scipy KD-tree, seeded sub-sampling)

@@ -1,7 +1,8 @@
 """Vertex-level parity as the metric `north_star` names (-m gpu): Chamfer distance (actionbench/chamfer.py restatement)
 between the per-frame vertices decoded from the B200 path's latents and from the REFERENCE's latents (golden 4-step
 CFG-7.5 trajectory produced by the reference's own SchedulerFlow + ActionMeshDenoiser), both decoded by the same fp32
-Stage-II decoder restatement (Stage II is out of scope for the CUDA path).  Vertices live in [-1, 1]^3."""
+Stage-II decoder restatement so that only the Stage-I difference is measured (the CUDA Stage II has its own parity
+test, tests/test_autoencoder_gpu.py).  Vertices live in [-1, 1]^3."""
 import json
 import os
 
