@@ -143,6 +143,79 @@ class B200Denoiser:
         return model
 
     # ------------------------------------------------------------------ weights
+    def _branch_program(self, ws: dict, st: WindowState, b: int, B: int, T: int, N: int, shard):
+        """Generator running the 21 blocks for ONE CFG branch of a frame-sharded window (rows [b*T*L, (b+1)*T*L) of every
+        workspace buffer; T = this rank's frames).  It yields right after launching the branch's K/V all-gather (and the
+        Q projection that does not depend on it); the caller round-robins the branches, so the gather of branch b,
+        layer l overlaps the other branch's attention + MLP.  The final block output of the branch is left in ws['h']."""
+        import torch.distributed as dist
+
+        c = self.config
+        w = self._w
+        D, H, dh = c.width, c.num_attention_heads, c.head_dim
+        L = N + 1
+        TL = T * L
+        rows = slice(b * TL, (b + 1) * TL)
+        scale = 1.0 / math.sqrt(dh)
+        h, xn, tmp = ws["h"][rows], ws["xn"][rows], ws["tmp"][rows]
+        qkv, att, ff = ws["qkv"][rows], ws["att"][rows], ws["ff"][rows]
+        kv_local, kv_all = ws["kv_local"][rows], ws["kv_all"][b]          # kv_all[b]: (world, TL, 2D)
+        rope_cos, rope_sin = st.rope_cos[b * T:(b + 1) * T], st.rope_sin[b * T:(b + 1) * T]
+        skips = [sk[rows] for sk in ws["skips"]]
+        sp = 0
+        half = c.num_layers // 2
+        h_in = h
+        S = st.ctx_kv[0].shape[0] // (B * T)
+        for i in range(c.num_layers):
+            p = f"blocks.{i}."
+            if i > half:
+                sp -= 1
+                ops.gemm(skips[sp], w[p + "skip.w"], tmp, a2=h_in, bias=w[p + "skip.b"])
+                ops.layernorm(tmp, w[p + "norm_skip.g"], w[p + "norm_skip.b"], 1e-5, out=h)
+                h_in = h
+            ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
+            if i in c.inflated_layers:
+                ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
+                         norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
+                                   rows_per_pos=L))
+                work = dist.all_gather_into_tensor(kv_all.view(-1, 2 * D), kv_local, group=shard.group, async_op=True)
+                ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
+                         norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
+                                   rows_per_pos=L))
+                yield
+                work.wait()
+                k5 = kv_all[None, :, :, 0:D].unflatten(-1, (H, dh))
+                v5 = kv_all[None, :, :, D:2 * D].unflatten(-1, (H, dh))
+                ops.flash_attn(qkv[:, 0:D].unflatten(-1, (H, dh))[None], k5, v5, att.view(1, TL, H, dh), scale,
+                               kv_chunks=shard.world, tag="attn_self")
+            else:
+                ops.gemm(xn, w[p + "s.qkv"], qkv,
+                         norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
+                                   cos=rope_cos, sin=rope_sin, rows_per_pos=L))
+                q4, k4, v4 = (qkv[:, j * D:(j + 1) * D].view(T, L, H, dh) for j in range(3))
+                ops.flash_attn(q4, k4, v4, att.view(T, L, H, dh), scale, tag="attn_self")
+            ops.gemm(att, w[p + "s.o.w"], h, bias=w[p + "s.o.b"], residual=h_in)
+            h_in = h
+            if st.ctx_zero[b]:
+                ops.add_bias_rows(h, w[p + "x.o.b"])
+            else:
+                ops.layernorm(h, w[p + "norm_x_attn.g"], w[p + "norm_x_attn.b"], 1e-5, out=xn)
+                qb = qkv[:, 0:D]
+                ops.gemm(xn, w[p + "x.q"], qb, norm=dict(cols=D, seg=D, w0=w[p + "x.nq"], eps=1e-6))
+                kvb = st.ctx_kv[i][b * T * S:(b + 1) * T * S]
+                ops.flash_attn(qb.view(T, L, H, dh), kvb[:, 0:D].view(T, S, H, dh), kvb[:, D:2 * D].view(T, S, H, dh),
+                               att.view(T, L, H, dh), scale, tag="attn_cross")
+                ops.gemm(att, w[p + "x.o.w"], h, bias=w[p + "x.o.b"], residual=h)
+            ops.layernorm(h, w[p + "norm_ff.g"], w[p + "norm_ff.b"], 1e-5, out=xn)
+            ops.gemm(xn, w[p + "ff1.w"], ff, bias=w[p + "ff1.b"], act=1)
+            if i < half:
+                ops.gemm(ff, w[p + "ff2.w"], skips[sp], bias=w[p + "ff2.b"], residual=h)
+                h_in = skips[sp]
+                sp += 1
+            else:
+                ops.gemm(ff, w[p + "ff2.w"], h, bias=w[p + "ff2.b"], residual=h)
+        assert h_in is h  # the last block is never a pushing block: its output lives in ws['h'] for the output head
+
     def load_state_dict(self, sd: dict) -> None:
         """Pack the reference's state dict (keys of SURVEY A.1) into kernel-ready device tensors: GEMM weights bf16
         (QKV / KV fused and head-permuted), biases / norm weights fp32."""
@@ -344,6 +417,22 @@ class B200Denoiser:
         ops.timestep_embedding(t32, D, out=ws["t_emb"], mask=m32, rows=B * T)
         ops.gemm(ws["t_emb"], w["time1.w"], ws["t_hid"], bias=w["time1.b"], act=1)
         ops.gemm(ws["t_hid"], w["time2.w"], h, bias=w["time2.b"], row_map=(1, L, 0))
+
+        if shard is not None and shard.world > 1 and B > 1 and os.environ.get("AMB_SHARD_STAGGER", "1") != "0":
+            # frame-sharded window with >1 CFG branch: the branches are independent through the whole network, so they
+            # run as two staggered programs on the one compute stream — while branch b's K/V all-gather is in flight
+            # the other branch runs its attention / MLP, which hides the gather completely (see _branch_program).
+            progs = [self._branch_program(ws, st, b, B, T, N, shard) for b in range(B)]
+            live = list(progs)
+            while live:
+                for g in list(live):
+                    try:
+                        next(g)
+                    except StopIteration:
+                        live.remove(g)
+            ops.layernorm(h, w["norm_out.g"], w["norm_out.b"], 1e-5, out=xn)
+            ops.gemm(xn, w["proj_out.w"], ws["pred"], bias=w["proj_out.b"])
+            return ws["pred"]
 
         # U-ViT long skips (temporal_denoiser.py:222-232) without copies: a pushing block writes its output straight
         # into a skip buffer, which then serves as the (read-only) residual input of the next block; the next block's

@@ -80,6 +80,15 @@ def main():
                 "forward_out_partial_inflate_nomask": out2, "t": t},
                os.path.join(GOLD, "denoiser_tiny.pt"))
 
+    # ---- the same 4-step trajectory under the reference's OWN mixed-precision recipe (pipeline.py:671 wraps the stages in
+    # torch.autocast(bf16)); run here with device_type="cpu" (same autocast op policy: linear/matmul/SDPA in bf16,
+    # layer_norm in fp32).  Yardstick for "how far is a bf16 path allowed to be from the fp32 path" in the Chamfer test.
+    with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+        den_ac = sch.denoise(m, cfg_b, lat.clone(), ctx, device="cpu", mask=mask, framestep=fs)
+    torch.save({"config": TINY, "seed": 1234, "input_seed": 5, "denoise4_out_autocast_bf16": den_ac.float(),
+                "rel_err_vs_fp32": float((den_ac.float()[0, 1:] - den[0, 1:]).norm() / den[0, 1:].norm())},
+               os.path.join(GOLD, "denoiser_tiny_autocast.pt"))
+
     # ---- full-width 3-layer model (covers the skip block at D=2048, 16 heads, F=8192, Dc=1024)
     mw = _model(ns, WIDE, 77)
     lat, ctx, fs, mask = synth.make_inputs(1, 2, 255, 64, 257, 1024, seed=6)
