@@ -49,6 +49,12 @@ class FrameShard:
     """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed."""
 
     def __init__(self, group=None):
+        if group is None and dist.get_backend() == "nccl" and os.environ.get("AMB_SHARD_HIPRI", "1") != "0":
+            # dedicated communicator on a HIGH-PRIORITY stream: the per-layer K/V all-gather has to run concurrently with
+            # compute kernels that fill every SM (persistent GEMMs, multi-wave attention); at normal priority its CTAs
+            # queue behind the pending compute CTAs and the gather is effectively serialised.
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            group = dist.new_group(ranks=list(range(dist.get_world_size())), pg_options=opts)
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
