@@ -162,6 +162,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from actionmesh_b200.window_shard import configure_nccl_env
+
+        configure_nccl_env()  # NCCL protocol / channel defaults for the sharded window's K/V all-gather (before init)
         dist.init_process_group("nccl", device_id=dev)
     K, W = args.steps, max(args.warmup, 0)
     T, N, C, S, Dc = 16, 2048, 64, 257, 1024

@@ -24,6 +24,9 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
+    from actionmesh_b200.window_shard import configure_nccl_env
+
+    configure_nccl_env()
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         from actionmesh_b200.denoiser import B200Denoiser, DenoiserConfig
