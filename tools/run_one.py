@@ -1,6 +1,6 @@
 """Launch one hot kernel at the default-window shape (for `ncu --set full` captures under gpurun).
 
-    python tools/run_one.py attn|attn_small|gemm_ff1|gemm_qkv [repeats]
+    python tools/run_one.py attn|attn_small|gemm_ff1|gemm_qkv|stage2 [repeats]
 """
 import math
 import os
@@ -42,5 +42,14 @@ elif which == "gemm_qkv":
     sin = torch.zeros(32, 64, device=dev)
     for _ in range(reps):
         ops.gemm(a, w, c, norm=dict(cols=4096, seg=2048, w0=w0, w1=w0, eps=1e-6, rope_cols=4096, cos=cos, sin=sin, rows_per_pos=2049))
+elif which == "stage2":  # the two HBM-bound kernels of the Stage-II fp32-grade query path at the default shape
+    R, Rp, D = 32784, 32832, 1024
+    s32 = torch.randn(2048, Rp, generator=g).to(dev)
+    p3 = torch.empty(2048, 3 * Rp, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(R, D, generator=g).to(dev)
+    x3 = torch.empty(R, 3 * D, device=dev, dtype=torch.bfloat16)
+    for _ in range(reps):
+        ops.softmax_split3(s32, R, 1 / math.sqrt(128), p3)
+        ops.split3(x, x3)
 torch.cuda.synchronize()
 print("done", which)
