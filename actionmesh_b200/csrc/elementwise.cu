@@ -281,51 +281,53 @@ __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ s
   }
 }
 
-// Row softmax of fp32 scores (one CTA per row, the row staged in shared memory), written as the A-pattern split
-// [P_hi | P_lo | P_hi] with each part n_pad wide and zeros in the padding columns [n, n_pad).
-__global__ void __launch_bounds__(512) softmax_split3_kernel(const float* __restrict__ s, long long ld_s, int n, int n_pad,
-                                                             float scale, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
-  extern __shared__ float row[];
-  __shared__ float red[16];
+// Row softmax of fp32 scores, written as the A-pattern split [P_hi | P_lo | P_hi] with each part n_pad wide and zeros in
+// the padding columns [n, n_pad).  One 512-thread CTA per row, two sweeps and no shared-memory staging of the row (an
+// earlier version staged the 131 KB row in shared memory, which capped occupancy at one CTA per SM = 25 % and 2.7 TB/s,
+// profiles/r01_ncu_gemm2_stage2_summary.txt): sweep 1 keeps a per-thread online (max, sum) pair, sweep 2 re-reads the row
+// (L2-resident: 4 CTAs/SM x 148 SMs x 131 KB = 78 MB) and writes exp(x - max) / sum.
+__global__ void __launch_bounds__(512, 4) softmax_split3_kernel(const float* __restrict__ s, long long ld_s, int n, int n_pad,
+                                                                float scale, __nv_bfloat16* __restrict__ dst, long long ld_dst) {
+  __shared__ float red_m[16], red_l[16];
   const float* src = s + (long long)blockIdx.x * ld_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float mx = -INFINITY;
-  for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {  // columns >= n (padding / ragged tail) are masked to -inf
+  float m = -INFINITY, l = 0.f;
+  for (int c = tid * 4; c < n; c += blockDim.x * 4) {  // columns >= n (padding / ragged tail) never enter the statistics
     float4 x = *reinterpret_cast<const float4*>(src + c);
-    x.x = (c + 0 < n) ? x.x * scale : -INFINITY;
+    x.x = x.x * scale;
     x.y = (c + 1 < n) ? x.y * scale : -INFINITY;
     x.z = (c + 2 < n) ? x.z * scale : -INFINITY;
     x.w = (c + 3 < n) ? x.w * scale : -INFINITY;
-    *reinterpret_cast<float4*>(row + c) = x;
-    mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+    const float m4 = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+    if (m4 > m) {
+      l *= expf(m - m4);  // m == -inf on the first visit: exp(-inf) == 0 and l == 0
+      m = m4;
+    }
+    l += (expf(x.x - m) + expf(x.y - m)) + (expf(x.z - m) + expf(x.w - m));
   }
+  // combine the (m, l) pairs of the CTA
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, red[w]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {
-    float4 x = *reinterpret_cast<const float4*>(row + c);
-    x.x = expf(x.x - mx); x.y = expf(x.y - mx); x.z = expf(x.z - mx); x.w = expf(x.w - mx);  // exp(-inf) == 0
-    *reinterpret_cast<float4*>(row + c) = x;
-    sum += (x.x + x.y) + (x.z + x.w);
+  for (int o = 16; o > 0; o >>= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o), lo = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, mo);
+    l = (mn == -INFINITY) ? 0.f : l * expf(m - mn) + lo * expf(mo - mn);
+    m = mn;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) red[warp] = sum;
+  if (lane == 0) { red_m[warp] = m; red_l[warp] = l; }
   __syncthreads();
-  sum = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
-  const float inv = 1.0f / sum;
+  float M = red_m[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) M = fmaxf(M, red_m[w]);
+  float L = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) L += (red_m[w] == -INFINITY) ? 0.f : red_l[w] * expf(red_m[w] - M);
+  const float inv = 1.0f / L;
   __nv_bfloat16* d = dst + (long long)blockIdx.x * ld_dst;
   for (int c = tid * 4; c < n_pad; c += blockDim.x * 4) {
+    const float4 x = *reinterpret_cast<const float4*>(src + c);
+    const float xs[4] = {x.x, x.y, x.z, x.w};
     __nv_bfloat16 hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float p = row[c + j] * inv;
+      const float p = (c + j < n) ? expf(xs[j] * scale - M) * inv : 0.f;
       hi[j] = __float2bfloat16_rn(p);
       lo[j] = __float2bfloat16_rn(p - __bfloat162float(hi[j]));
     }
@@ -461,15 +463,8 @@ int amb_softmax_split3(const float* scores, int64_t ld_s, int rows, int n, int n
   AMB_CHECK_ARG(scores && dst_bf16, "softmax_split3: null pointer");
   AMB_CHECK_ARG(n > 0 && n_pad >= n && n_pad % 4 == 0 && ld_s % 4 == 0 && ld_s >= n_pad && ld_dst % 4 == 0 && ld_dst >= 3LL * n_pad,
                 "softmax_split3: bad geometry n=%d n_pad=%d", n, n_pad);
-  const size_t smem = (size_t)n_pad * sizeof(float);
-  AMB_CHECK_ARG(smem <= 200 * 1024, "softmax_split3: row of %d scores does not fit shared memory", n);
   if (rows <= 0) return AMB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMB_CHECK_CUDA(cudaFuncSetAttribute(softmax_split3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  softmax_split3_kernel<<<rows, 512, smem, (cudaStream_t)stream>>>(scores, ld_s, n, n_pad, scale,
+  softmax_split3_kernel<<<rows, 512, 0, (cudaStream_t)stream>>>(scores, ld_s, n, n_pad, scale,
                                                                   reinterpret_cast<__nv_bfloat16*>(dst_bf16), ld_dst);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;

@@ -8,8 +8,9 @@ kernels: patchify (im2col) -> tcgen05 GEMM, LayerNorm, fused-QKV tcgen05 GEMM, t
 GEMM epilogues with bias / GELU / LayerScale / fp32 residual.  The residual stream is kept in fp32 (the reference runs
 DinoV2 in fp32, outside autocast, pipeline.py:664-667); GEMM operands are bf16 with fp32 accumulation.
 
-Image preprocessing stays on the host exactly like the reference (HF BitImageProcessor: bicubic resize to 256, centre
-crop 224, 1/255 rescale, ImageNet mean/std); it is listed as "next" in SURVEY 8(f).
+Image preprocessing (HF BitImageProcessor in the reference: bicubic resize to 256, centre crop 224, 1/255 rescale, ImageNet
+mean/std) runs on the GPU with the semantics of the reference's pinned transformers<5 / Pillow path, bit-exact on the uint8
+image (actionmesh_b200/preprocess.py); `image_preprocess_dino` keeps the HF object as the source of the configuration.
 """
 from __future__ import annotations
 
@@ -51,6 +52,7 @@ class B200ImageEncoder:
         self._loaded = False
         self._pending_sd = None
         self.image_preprocess_dino = None
+        self._gpu_preprocess = None
         if pretrained_dino_feature_extractor is not None and os.path.isdir(pretrained_dino_feature_extractor):
             from transformers import BitImageProcessor
             self.image_preprocess_dino = BitImageProcessor.from_pretrained(pretrained_dino_feature_extractor)
@@ -157,8 +159,11 @@ class B200ImageEncoder:
     @torch.no_grad()
     def encode_images(self, images: List) -> torch.Tensor:
         """images: list of T PIL images -> context (T, 257, 1024) fp32 (image_encoder.py:38-55)."""
-        pixel_values = self.image_preprocess_dino.preprocess(images, return_tensors="pt").pixel_values
-        return self.encode_pixel_values(pixel_values)
+        if self._gpu_preprocess is None:
+            from .preprocess import B200ImagePreprocessor
+
+            self._gpu_preprocess = B200ImagePreprocessor.from_hf(self.image_preprocess_dino)
+        return self.encode_pixel_values(self._gpu_preprocess.preprocess(images, self._device))
 
     @torch.no_grad()
     def encode_pixel_values(self, pixel_values: torch.Tensor) -> torch.Tensor:

@@ -174,6 +174,50 @@ def displacement_out(logits: torch.Tensor, out_dim: int, out: torch.Tensor) -> t
     return out
 
 
+def resize_h_u8(src: torch.Tensor, y0: int, n_rows: int, bounds: torch.Tensor, coeffs: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """Horizontal pass of Pillow's uint8 resample on source rows [y0, y0+n_rows): src (n, H, W, 3|4) u8 -> out (n, n_rows, out_w, 3)."""
+    global launch_count
+    _need(src, torch.uint8, "src")
+    _need(out, torch.uint8, "out")
+    _need(bounds, torch.int32, "bounds")
+    _need(coeffs, torch.int32, "coeffs")
+    assert src.dim() == 4 and src.is_contiguous() and out.is_contiguous() and bounds.is_contiguous() and coeffs.is_contiguous()
+    n, H, W, cin = src.shape
+    out_w, ksize = coeffs.shape
+    assert out.shape == (n, n_rows, out_w, 3) and bounds.shape == (out_w, 2)
+    rc = _lib.load_library().amb_resize_h_u8(src.data_ptr(), n, H, W, cin, y0, n_rows, bounds.data_ptr(), coeffs.data_ptr(),
+                                             ksize, out_w, out.data_ptr(), _stream())
+    _lib.check(rc, "amb_resize_h_u8")
+    launch_count += 1
+    return out
+
+
+def resize_v_normalize(src: torch.Tensor, y0: int, bounds: torch.Tensor, coeffs: torch.Tensor, lut: torch.Tensor, mean, std,
+                       out: torch.Tensor, out_u8: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Vertical pass + 1/255 rescale (lut) + mean/std + CHW: src (n, n_rows, out_w, 3) u8 -> out (n, 3, out_h, out_w) fp32."""
+    global launch_count
+    _need(src, torch.uint8, "src")
+    _need(out, torch.float32, "out")
+    _need(bounds, torch.int32, "bounds")
+    _need(coeffs, torch.int32, "coeffs")
+    _need(lut, torch.float32, "lut")
+    assert src.is_contiguous() and out.is_contiguous() and lut.numel() == 256
+    n, n_rows, out_w, _ = src.shape
+    out_h, ksize = coeffs.shape
+    assert out.shape == (n, 3, out_h, out_w) and bounds.shape == (out_h, 2)
+    if out_u8 is not None:
+        _need(out_u8, torch.uint8, "out_u8")
+        assert out_u8.shape == (n, out_h, out_w, 3) and out_u8.is_contiguous()
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    s = (C.c_float * 3)(*[float(v) for v in std])
+    rc = _lib.load_library().amb_resize_v_normalize(src.data_ptr(), n, n_rows, y0, out_w, bounds.data_ptr(), coeffs.data_ptr(),
+                                                    ksize, out_h, lut.data_ptr(), m, s, out.data_ptr(),
+                                                    out_u8.data_ptr() if out_u8 is not None else None, _stream())
+    _lib.check(rc, "amb_resize_v_normalize")
+    launch_count += 1
+    return out
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global launch_count
     _need(src, torch.float32, "src")

@@ -287,7 +287,7 @@ def run_b200(args):
                             "layer over NCCL (window_shard.py); steps/s of that single window"}
 
     # ---------------- sec/video of the Stage-I path through the public pipeline API (N = 1 only): 16 synthetic RGB frames
-    # -> BitImageProcessor -> DinoV2-L -> one 16-frame window, default 30 steps, CFG 7.5 (Stage 0 / Stage II out of scope)
+    # -> CUDA preprocessing (PIL-exact bicubic resize/crop/normalise) -> DinoV2-L -> one 16-frame window, default 30 steps, CFG 7.5 (Stage 0 / Stage II out of scope)
     video = None
     if world == 1 and not args.no_video:
         import numpy as np
@@ -315,7 +315,7 @@ def run_b200(args):
         t2 = time.perf_counter()
         video = {"sec_per_video_stage1": t2 - t0, "dinov2_encode_s": t1 - t0, "denoise_30_steps_s": t2 - t1,
                  "frames": T, "steps": 30, "finite": bool(torch.isfinite(lat_host).all()),
-                 "note": "Stage-I path only (DinoV2 encode incl. host BitImageProcessor + 1 window x 30 steps, CFG 7.5) through "
+                 "note": "Stage-I path only (uint8 frames -> CUDA BitImageProcessor-equivalent preprocessing -> DinoV2 + 1 window x 30 steps, CFG 7.5) through "
                          "Stage1Pipeline; Stage 0 (TripoSG) is out of scope and not included; Stage II is timed separately below"}
         del enc, pipe
         # Stage II on the same window: 16-block trunk re-run for each of the 15 target times + the

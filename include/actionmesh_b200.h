@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 7
+#define AMB_ABI_VERSION 8
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -68,6 +68,23 @@ int amb_patchify(const float* pixels, void* out_bf16, int n_images, int height, 
 int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows, int channels, void* out_bf16,
                            amb_stream_t stream);
 int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream);
+
+/* ---- image preprocessing for the DinoV2 encoder (on row a2's path) -------------------------------
+ * Replaces the host BitImageProcessor call at actionmesh/model/image_encoder.py:48-51 (transformers < 5, requirements.txt:10:
+ * PIL bicubic resize -> centre crop -> x 1/255 -> mean/std -> CHW).  Pillow's uint8 resize is a two-pass separable integer
+ * convolution (libImaging/Resample.c): int32 coefficients with 22 fractional bits, accumulator seeded with 1 << 21,
+ * (acc >> 22) clamped to [0, 255], uint8 between the passes; both passes are reproduced bit-exactly.
+ *  resize_h_u8: src (n, in_h, in_w, channels_in in {3,4}) u8 -> dst (n, n_rows, out_w, 3) u8 for source rows [y0, y0+n_rows);
+ *    bounds (out_w, 2) = (first source column, tap count), coeffs (out_w, ksize) — host-built, already restricted to the
+ *    cropped output window.  All table entries must address columns inside [0, in_w).
+ *  resize_v_normalize: src as written by resize_h_u8 -> dst (n, 3, out_h, out_w) fp32 = (lut256[u8] - mean[c]) / std[c];
+ *    bounds (out_h, 2) in SOURCE row numbers, every tap inside [y0, y0+n_rows); mean/std are HOST pointers to 3 floats;
+ *    dst_u8 (optional, may be NULL) receives the resized+cropped uint8 image (n, out_h, out_w, 3). */
+int amb_resize_h_u8(const uint8_t* src, int n_images, int in_h, int in_w, int channels_in, int y0, int n_rows,
+                    const int32_t* bounds, const int32_t* coeffs, int ksize, int out_w, uint8_t* dst, amb_stream_t stream);
+int amb_resize_v_normalize(const uint8_t* src, int n_images, int n_rows, int y0, int out_w, const int32_t* bounds,
+                           const int32_t* coeffs, int ksize, int out_h, const float* lut256, const float* mean3_host,
+                           const float* std3_host, float* dst, uint8_t* dst_u8, amb_stream_t stream);
 
 /* ---- Stage II (temporal autoencoder) helpers — first "next" row of SURVEY 8(f) -----------------------------------------
  * alpha_rows: the (source_alpha, target_alpha) token of actionmesh/model/temporal_autoencoder.py:233-237 (TimestepEmbedder,

@@ -40,7 +40,8 @@ def test_dinov2_large_matches_hf(amb_lib):
 
 
 def test_encode_images_pil_surface(amb_lib):
-    """encode_images(list[PIL]) goes through the HF BitImageProcessor like the reference (image_encoder.py:48-51)."""
+    """encode_images(list[PIL]) == BitImageProcessor (transformers<5 / Pillow semantics, oracle/preprocess_oracle.py) followed
+    by DinoV2, like the reference (image_encoder.py:48-55); the preprocessing itself runs in CUDA (tests/test_preprocess_gpu.py)."""
     from PIL import Image
     import numpy as np
 
@@ -48,6 +49,8 @@ def test_encode_images_pil_surface(amb_lib):
     rng = np.random.default_rng(7)
     imgs = [Image.fromarray(rng.integers(0, 255, (512, 512, 3), dtype=np.uint8), "RGB") for _ in range(2)]
     out = enc.encode_images(imgs)
-    px = enc.image_preprocess_dino.preprocess(imgs, return_tensors="pt").pixel_values
+    from oracle import preprocess_oracle
+
+    px = torch.from_numpy(preprocess_oracle.bit_preprocess_pil(imgs))
     assert px.shape == (2, 3, 224, 224)
     assert rel(out, dinov2_oracle.encode(ref, px)) < 1e-2
