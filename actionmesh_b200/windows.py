@@ -96,3 +96,80 @@ class LatentBank:
         order = sorted(range(len(self.timesteps)), key=lambda i: self.timesteps[i])
         lat = torch.stack([self.items[i] for i in order])
         return lat, torch.tensor([self.timesteps[i] for i in order]).to(lat)
+
+    def get_ordered_timesteps(self) -> torch.Tensor:
+        """storage.py TimestepIndexedStorage.get_ordered_timesteps: all stored timesteps, ascending (fp32, CPU)."""
+        return torch.tensor(sorted(self.timesteps), dtype=torch.float32)
+
+
+class VertexBank:
+    """Timestep-indexed store of per-frame vertex arrays — the role `MeshBank` (storage.py:187-260) plays in Stage II.
+    The reference stores trimesh objects that all share the anchor's faces; only the vertices change, so this bank keeps
+    (V, 3) fp32 tensors and one shared `faces` array the caller may attach."""
+
+    def __init__(self, faces=None):
+        self.items: list[torch.Tensor] = []
+        self.timesteps: list[float] = []
+        self.faces = faces
+
+    @property
+    def n_timesteps(self) -> int:
+        return len(self.timesteps)
+
+    def get_timestep_index(self, timestep: float, eps: float = 1e-5):
+        for i, ts in enumerate(self.timesteps):
+            if abs(ts - timestep) < eps:
+                return i
+        return None
+
+    def update(self, timesteps: torch.Tensor, vertices, replace: bool = False) -> None:
+        ts = [float(t) for t in timesteps.flatten().tolist()]
+        assert len(ts) == len(vertices)
+        for i, t in enumerate(ts):
+            idx = self.get_timestep_index(t)
+            if idx is None:
+                self.timesteps.append(t)
+                self.items.append(vertices[i])
+            elif replace:
+                self.items[idx] = vertices[i]
+
+    def get(self, timesteps: torch.Tensor) -> list:
+        assert timesteps.ndim == 1
+        out = []
+        for t in timesteps.tolist():
+            idx = self.get_timestep_index(t)
+            out.append(self.items[idx] if idx is not None else None)
+        return out
+
+    def get_ordered(self):
+        order = sorted(range(len(self.timesteps)), key=lambda i: self.timesteps[i])
+        return [self.items[i] for i in order], torch.tensor([self.timesteps[i] for i in order], dtype=torch.float32)
+
+
+# ---- Stage-II time bookkeeping (actionmesh/model/utils/embeddings.py:156-242) ------------------------------------------
+def get_scaling(timesteps: torch.Tensor):
+    """embeddings.py:156-173: per-batch (min, max - min) of (B, T) timesteps."""
+    t_min = timesteps.min(dim=1).values
+    return t_min, timesteps.max(dim=1).values - t_min
+
+
+def apply_scaling(timesteps: torch.Tensor, t_min: torch.Tensor, t_range: torch.Tensor) -> torch.Tensor:
+    """embeddings.py:176-196: (t - t_min) / t_range, for (B,) or (B, T) inputs."""
+    if timesteps.dim() == 1:
+        return (timesteps - t_min) / t_range
+    return (timesteps - t_min.unsqueeze(1)) / t_range.unsqueeze(1)
+
+
+def get_n_subdivisions(start, end, level: int = 1) -> int:
+    """embeddings.py:199-214: number of points after `level - 1` rounds of midpoint insertion."""
+    n_points = int(end - start + 1)
+    for _ in range(1, level):
+        n_points += n_points - 1
+    return n_points
+
+
+def interpolate_timesteps(timesteps: torch.Tensor, subsampling_level: int, device="cpu", drop_first: bool = False) -> torch.Tensor:
+    """embeddings.py:217-242: linspace(min, max, n_subdivisions) as (1, n) [(1, n-1) with drop_first]."""
+    t_min, t_max = timesteps.min().item(), timesteps.max().item()
+    out = torch.linspace(t_min, t_max, get_n_subdivisions(t_min, t_max, level=subsampling_level), device=device).reshape(1, -1)
+    return out[:, 1:] if drop_first else out

@@ -132,6 +132,49 @@ def apply_displacement(vertex, displacement, mode="direct", scale=1.0):
     return (vertex[:, None] + displacement).clamp(-scale, scale)
 
 
+# ---- Stage-II orchestration (pipeline.py:510-600 generate_mesh_animation + :316-385 _decode_displacement) ------------------
+def get_n_subdivisions(start, end, level=1):
+    """embeddings.py:199-214."""
+    n = int(end - start + 1)
+    for _ in range(1, level):
+        n += n - 1
+    return n
+
+
+def interpolate_timesteps(timesteps, subsampling_level, drop_first=False):
+    """embeddings.py:217-242."""
+    t_min, t_max = timesteps.min().item(), timesteps.max().item()
+    out = torch.linspace(t_min, t_max, get_n_subdivisions(t_min, t_max, subsampling_level)).reshape(1, -1)
+    return out[:, 1:] if drop_first else out
+
+
+def generate_mesh_animation(decode, latents, timesteps, anchor_vertices, anchor_normals, *, anchor_idx=0, context_size=16,
+                            slide=15, subsampling_level=1, normals_fn=None):
+    """pipeline.py:510-600 with the mesh bank reduced to {timestep: (V,3) vertices} (all meshes share the anchor faces).
+    `decode(latent (1,T,N,C), framestep (1,T), source_alpha (1,), target_alphas (1,T_out), query (1,V,6)) -> (1,T_out,V,3)`
+    displacement; returns (sorted timesteps, [vertices])."""
+    order = torch.argsort(timesteps)
+    all_ts, lat_sorted = timesteps[order], latents[order]
+    bank = {float(timesteps[anchor_idx]): anchor_vertices}
+    for idx in do.chunk_from(anchor_idx, len(all_ts), context_size, slide):
+        wts = all_ts[idx][None]
+        verts = bank[float(wts[0, 0])]
+        first = abs(float(wts[0, 0]) - float(timesteps[anchor_idx])) < 1e-5
+        normals = anchor_normals if first else normals_fn(verts)
+        out_ts = interpolate_timesteps(wts, subsampling_level, drop_first=True)
+        t_min = wts.min(dim=1).values
+        t_range = wts.max(dim=1).values - t_min                                      # embeddings.py:156-196
+        src = (wts[:, 0] - t_min) / t_range
+        tgt = (out_ts - t_min[:, None]) / t_range[:, None]
+        q = torch.cat([verts, normals], dim=-1)[None]
+        v = apply_displacement(verts[None], decode(lat_sorted[idx][None], wts, src, tgt, q))[0]
+        for j, t in enumerate(out_ts[0].tolist()):
+            if not any(abs(t - k) < 1e-5 for k in bank):
+                bank[t] = v[j]
+    ts = sorted(bank)
+    return ts, [bank[t] for t in ts]
+
+
 def chamfer_score(pred, gt, n: int = 10_000, seed: int = 44) -> float:
     """actionbench/chamfer.py:12-50: symmetric Chamfer distance, seeded sub-sampling of the query sets, KD-tree NN."""
     from scipy.spatial import KDTree

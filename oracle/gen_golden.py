@@ -63,6 +63,18 @@ def main():
     host["bank_get"] = (lat, msk)
     torch.save(host, os.path.join(GOLD, "host_logic.pt"))
 
+    # ---- Stage-II time bookkeeping (reference embeddings.py:156-242, imported unchanged)
+    E = ns.embeddings
+    s2 = {"n_subdivisions": {(a, b, l): E.get_n_subdivisions(a, b, l) for a, b, l in ((0, 15, 1), (0.0, 15.0, 2), (3, 18, 3), (5.0, 5.0, 1))},
+          "interp": {}, "scaling": {}}
+    for name, ts in (("w16", torch.arange(16.0)[None]), ("w16_off", torch.arange(15.0, 31.0)[None]), ("w5", torch.tensor([[2.0, 3.0, 4.0, 5.0, 6.0]]))):
+        for lvl in (1, 2):
+            for df in (False, True):
+                s2["interp"][(name, lvl, df)] = E.interpolate_timesteps(ts, subsampling_level=lvl, device="cpu", drop_first=df)
+        t_min, t_range = E.get_scaling(ts)
+        s2["scaling"][name] = (ts, t_min, t_range, E.apply_scaling(ts[:, 0], t_min, t_range), E.apply_scaling(ts, t_min, t_range))
+    torch.save(s2, os.path.join(GOLD, "stage2_host_logic.pt"))
+
     # ---- tiny denoiser: forward + 4-step CFG denoise through the reference scheduler
     m = _model(ns, TINY, 1234)
     lat, ctx, fs, mask = synth.make_inputs(1, 3, 31, 64, 9, 128, seed=5)

@@ -39,6 +39,7 @@ def load():
     from actionmesh.model.temporal_denoiser import ActionMeshDenoiser
     from actionmesh.model.utils.attention_processor import AttentionProcessor
     from actionmesh.model.utils.block import FlowMatchingBlock
+    from actionmesh.model.utils import embeddings as ref_embeddings
     from actionmesh.model.utils.rotary_embedding import apply_rotary_embedding, compute_rotary_embeddings
     from actionmesh.model.utils.storage import LatentBank
     from actionmesh.model.utils.timesteps import chunk_from
@@ -50,5 +51,6 @@ def load():
         FlowMatchingBlock=FlowMatchingBlock, apply_rotary_embedding=apply_rotary_embedding,
         compute_rotary_embeddings=compute_rotary_embeddings, LatentBank=LatentBank, chunk_from=chunk_from,
         ClassifierFreeGuidance=ClassifierFreeGuidance, SchedulerFlow=SchedulerFlow, torch=torch,
+        embeddings=ref_embeddings,
     )
     return ns

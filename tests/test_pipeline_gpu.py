@@ -54,3 +54,39 @@ def test_two_window_autoregressive_latents_match_oracle(amb_lib):
     assert err < 3e-2, err
     # window 2 really was conditioned on window 1's last frame: its first frame is the overlap frame, bit-identical
     assert len(pipe.temporal_3D_denoiser._ws) == 1 and not calls
+
+
+def test_stage2_animation_windows_match_oracle(amb_lib):
+    """AnimationPipeline.generate_mesh_animation (pipeline.py:510-600) on the CUDA autoencoder vs the oracle restatement
+    driving the fp32 oracle decoder: 7 latent frames decoded in windows of 4 (slide 3) => 2 serial windows, the second one
+    anchored on a mesh the first one produced (vertex normals recomputed by the caller-supplied normals_fn)."""
+    from actionmesh_b200.autoencoder import AutoencoderConfig, B200Autoencoder
+    from actionmesh_b200.pipeline import AnimationPipeline
+    from actionmesh_b200.windows import LatentBank, VertexBank
+    from oracle import autoencoder_oracle as ao
+
+    ocfg = ao.AutoencoderConfig(width=256, num_layers=2, num_attention_heads=2)
+    sd = ao.make_autoencoder_state_dict(ocfg, 99)
+    ae = B200Autoencoder(AutoencoderConfig(width=256, num_layers=2, num_attention_heads=2, temporal_context_size=4)).to("cuda")
+    ae.load_state_dict(sd)
+    g = torch.Generator().manual_seed(21)
+    n_frames, N, V = 7, 31, 500
+    lat = torch.randn(n_frames, N, 64, generator=g)
+    ts = torch.arange(n_frames, dtype=torch.float32)
+    verts = torch.randn(V, 3, generator=g)
+    verts = verts / verts.norm(dim=-1, keepdim=True) * 0.5
+    nfn = lambda v: torch.nn.functional.normalize(v.float().cpu(), dim=-1)   # a sphere-like cloud: normal ~ direction
+    pipe = AnimationPipeline.__new__(AnimationPipeline)
+    pipe.temporal_3D_vae = pipe.temporal_3D_denoiser = ae
+    pipe.anchor_idx, pipe.sliding_window_autoencoder, pipe.subsampling_level, pipe.normals_fn = 0, 3, 1, nfn
+    bank = LatentBank(empty_dims=(N, 64))
+    bank.update(timesteps=ts, latents=lat)
+    vb = VertexBank()
+    vb.update(timesteps=ts[0:1], vertices=[verts])
+    got_v, got_t = pipe.generate_mesh_animation(bank, vb, nfn(verts)).get_ordered()
+    dec = lambda latent, framestep, source_alpha, target_alphas, query: ao.autoencoder_forward(
+        sd, ocfg, latent, framestep, source_alpha, target_alphas, query)
+    ref_t, ref_v = ao.generate_mesh_animation(dec, lat, ts, verts, nfn(verts), anchor_idx=0, context_size=4, slide=3, normals_fn=nfn)
+    assert got_t.tolist() == ref_t and len(got_v) == n_frames
+    err = max(float((a.float().cpu() - b).abs().max()) for a, b in zip(got_v, ref_v))
+    assert err < 2e-2, err
