@@ -418,10 +418,10 @@ class B200Denoiser:
         ops.gemm(ws["t_emb"], w["time1.w"], ws["t_hid"], bias=w["time1.b"], act=1)
         ops.gemm(ws["t_hid"], w["time2.w"], h, bias=w["time2.b"], row_map=(1, L, 0))
 
-        if shard is not None and shard.world > 1 and B > 1 and os.environ.get("AMB_SHARD_STAGGER", "1") != "0":
-            # frame-sharded window with >1 CFG branch: the branches are independent through the whole network, so they
-            # run as two staggered programs on the one compute stream — while branch b's K/V all-gather is in flight
-            # the other branch runs its attention / MLP, which hides the gather completely (see _branch_program).
+        if shard is not None and shard.world > 1:
+            # frame-sharded window: the CFG branches are independent through the whole network, so they run as staggered
+            # programs on the one compute stream — while branch b's K/V all-gather is in flight the other branch runs its
+            # attention / MLP (see _branch_program).  Everything below this block is the single-GPU path.
             progs = [self._branch_program(ws, st, b, B, T, N, shard) for b in range(B)]
             live = list(progs)
             while live:
@@ -451,39 +451,14 @@ class B200Denoiser:
             # ---- self-attention (block.py:137-142, attention_processor.py:49-166)
             ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
             inflated = i in c.inflated_layers
-            if shard is not None and shard.world > 1 and inflated:
-                # frame-sharded window: K/V of this rank's frames -> NCCL all-gather -> attention over `world` chunks;
-                # the Q projection runs while the gather is in flight.
-                import torch.distributed as dist
-                kv_local, kv_all = ws["kv_local"], ws["kv_all"]
-                ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
-                         norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
-                                   sin=st.rope_sin, rows_per_pos=L))
-                # one all-gather per CFG branch (contiguous row blocks), so the attention of branch b overlaps the
-                # gather of branch b+1; kv_all is (B, world, T_local*L, 2D): chunk c of a branch = rank c's frames
-                TLl = T * L
-                works = [dist.all_gather_into_tensor(kv_all[b].view(-1, 2 * D), kv_local[b * TLl:(b + 1) * TLl],
-                                                     group=shard.group, async_op=True) for b in range(B)]
-                ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
-                         norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=st.rope_cos,
-                                   sin=st.rope_sin, rows_per_pos=L))
-                for b in range(B):
-                    works[b].wait()
-                    kvb = kv_all[b]                                              # (world, TLl, 2D)
-                    k5 = kvb[None, :, :, 0:D].unflatten(-1, (H, dh))             # (1, world, TLl, H, dh)
-                    v5 = kvb[None, :, :, D:2 * D].unflatten(-1, (H, dh))
-                    q4 = qkv[b * TLl:(b + 1) * TLl, 0:D].unflatten(-1, (H, dh))[None]
-                    ops.flash_attn(q4, k5, v5, att[b * TLl:(b + 1) * TLl].view(1, TLl, H, dh), scale,
-                                   kv_chunks=shard.world, tag="attn_self")
-            else:
-                ops.gemm(xn, w[p + "s.qkv"], qkv,
-                         norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
-                                   cos=st.rope_cos, sin=st.rope_sin, rows_per_pos=L))
-                view = (B, T * L, H, dh) if inflated else (B * T, L, H, dh)
-                q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-                k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-                v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
-                ops.flash_attn(q4, k4, v4, att.view(*view), scale, tag="attn_self")
+            ops.gemm(xn, w[p + "s.qkv"], qkv,
+                     norm=dict(cols=2 * D, seg=D, w0=w[p + "s.nq"], w1=w[p + "s.nk"], eps=1e-6, rope_cols=2 * D,
+                               cos=st.rope_cos, sin=st.rope_sin, rows_per_pos=L))
+            view = (B, T * L, H, dh) if inflated else (B * T, L, H, dh)
+            q4 = qkv[:, 0:D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            k4 = qkv[:, D:2 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            v4 = qkv[:, 2 * D:3 * D].unflatten(0, view[:2]).unflatten(-1, (H, dh))
+            ops.flash_attn(q4, k4, v4, att.view(*view), scale, tag="attn_self")
             ops.gemm(att, w[p + "s.o.w"], h, bias=w[p + "s.o.b"], residual=h_in)
             h_in = h
             # ---- cross-attention (block.py:146-149); zero-context batch elements reduce to + to_out.0.bias (A.5)
