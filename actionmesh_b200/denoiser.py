@@ -219,10 +219,13 @@ class B200Denoiser:
     def load_state_dict(self, sd: dict) -> None:
         """Pack the reference's state dict (keys of SURVEY A.1) into kernel-ready device tensors: GEMM weights bf16
         (QKV / KV fused and head-permuted), biases / norm weights fp32."""
-        c = self.config
-        dev = self._device
-        if dev.type != "cuda":
+        if self._device.type != "cuda":
             raise AmbError("call .to('cuda') before load_state_dict")
+        self._w = self._pack_state_dict(sd, self._device)
+        self._loaded = True
+
+    def _pack_state_dict(self, sd: dict, dev: torch.device) -> dict:
+        c = self.config
         H = c.num_attention_heads
 
         def W(name):  # GEMM operand
@@ -256,8 +259,7 @@ class B200Denoiser:
             w[p + "x.o.w"], w[p + "x.o.b"] = W(p + "x_attn.to_out.0.weight"), V(p + "x_attn.to_out.0.bias")
             w[p + "ff1.w"], w[p + "ff1.b"] = W(p + "ff.net.0.proj.weight"), V(p + "ff.net.0.proj.bias")
             w[p + "ff2.w"], w[p + "ff2.b"] = W(p + "ff.net.2.weight"), V(p + "ff.net.2.bias")
-        self._w = w
-        self._loaded = True
+        return w
 
     def init_random_(self, seed: int = 1234, residual_scale: Optional[float] = None) -> None:
         """Synthetic weights for benchmarks (no checkpoints offline): torch default Linear/LayerNorm inits, residual

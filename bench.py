@@ -257,96 +257,102 @@ def run_b200(args):
     # ---------------- N > 1: also time ONE window frame-sharded over all ranks (strong scaling, K/V all-gather)
     temporal = None
     if world > 1 and 16 % world == 0:
-        from actionmesh_b200.window_shard import FrameShard
+        try:
+            from actionmesh_b200.window_shard import FrameShard
 
-        shard = FrameShard()
-        g0 = torch.Generator(device="cpu").manual_seed(44)
-        lat_t = torch.randn(1, T, N, C, generator=g0).to(dev)      # identical window on every rank
-        ctx_t = torch.randn(1, T, S, Dc, generator=torch.Generator().manual_seed(5)).to(dev)
-        sch3 = B200SchedulerFlow(num_inference_steps=W + K, shift=3.0, is_additive=True)
-        ev3 = {}
+            shard = FrameShard()
+            g0 = torch.Generator(device="cpu").manual_seed(44)
+            lat_t = torch.randn(1, T, N, C, generator=g0).to(dev)      # identical window on every rank
+            ctx_t = torch.randn(1, T, S, Dc, generator=torch.Generator().manual_seed(5)).to(dev)
+            sch3 = B200SchedulerFlow(num_inference_steps=W + K, shift=3.0, is_additive=True)
+            ev3 = {}
 
-        def cb3(step, total):
-            if step == W:
-                ev3["t0"] = torch.cuda.Event(enable_timing=True)
-                ev3["t0"].record()
-            if step == total:
-                ev3["t1"] = torch.cuda.Event(enable_timing=True)
-                ev3["t1"].record()
+            def cb3(step, total):
+                if step == W:
+                    ev3["t0"] = torch.cuda.Event(enable_timing=True)
+                    ev3["t0"].record()
+                if step == total:
+                    ev3["t1"] = torch.cuda.Event(enable_timing=True)
+                    ev3["t1"].record()
 
-        barrier()
-        if W == 0:
-            cb3(0, W + K)
-        sch3.denoise(model, cf, lat_t, ctx_t, device=dev, mask=mask, framestep=framestep, step_callback=cb3, shard=shard)
-        barrier()
-        t3 = torch.tensor([ev3["t0"].elapsed_time(ev3["t1"])], device=dev, dtype=torch.float64)
-        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
-        temporal = {"value": K / (float(t3.item()) / 1e3), "unit": UNIT, "ms_per_step": float(t3.item()) / K,
-                    "scaling": "strong", "frames_per_rank": T // world,
-                    "note": "ONE default window, frames sharded over the ranks, temporal-attention K/V all-gathered per "
-                            "layer over NCCL (window_shard.py); steps/s of that single window"}
+            barrier()
+            if W == 0:
+                cb3(0, W + K)
+            sch3.denoise(model, cf, lat_t, ctx_t, device=dev, mask=mask, framestep=framestep, step_callback=cb3, shard=shard)
+            barrier()
+            t3 = torch.tensor([ev3["t0"].elapsed_time(ev3["t1"])], device=dev, dtype=torch.float64)
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+            temporal = {"value": K / (float(t3.item()) / 1e3), "unit": UNIT, "ms_per_step": float(t3.item()) / K,
+                        "scaling": "strong", "frames_per_rank": T // world,
+                        "note": "ONE default window, frames sharded over the ranks, temporal-attention K/V all-gathered per "
+                                "layer over NCCL (window_shard.py); steps/s of that single window"}
+        except Exception as exc:  # noqa: BLE001 - an optional leg must never cost the main JSON line
+            temporal = {"error": f"{type(exc).__name__}: {exc}"[:400]}
 
     # ---------------- sec/video of the Stage-I path through the public pipeline API (N = 1 only): 16 synthetic RGB frames
-    # -> CUDA preprocessing (PIL-exact bicubic resize/crop/normalise) -> DinoV2-L -> one 16-frame window, default 30 steps, CFG 7.5 (Stage 0 / Stage II out of scope)
+    # -> CUDA preprocessing (PIL-exact bicubic resize/crop/normalise) -> DinoV2-L -> one 16-frame window, default 30 steps, CFG 7.5; then Stage II (Stage 0 out of scope)
     video = None
     if world == 1 and not args.no_video:
-        import numpy as np
-        from PIL import Image
+        try:
+            import numpy as np
+            from PIL import Image
 
-        from actionmesh_b200.image_encoder import B200ImageEncoder
-        from actionmesh_b200.pipeline import Stage1Pipeline, VideoInput
+            from actionmesh_b200.image_encoder import B200ImageEncoder
+            from actionmesh_b200.pipeline import Stage1Pipeline, VideoInput
 
-        enc = B200ImageEncoder().to(dev)
-        enc.init_random_(seed=1235)  # DinoV2-L/14 shape, seeded random weights (no checkpoints offline)
-        rng = np.random.default_rng(7)
-        frames = [Image.fromarray(rng.integers(0, 255, (512, 512, 3), dtype=np.uint8), "RGB") for _ in range(T)]
-        pipe = Stage1Pipeline(model, B200SchedulerFlow(num_inference_steps=30, shift=3.0, is_additive=True), cf, enc)
-        anchor = torch.randn(1, N, C, generator=torch.Generator().manual_seed(99))
-        vin = VideoInput(frames, torch.arange(T, dtype=torch.float32))
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        ctx_v = pipe.encode_all_frames(vin)
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        bank = pipe(vin, anchor, seed=44, stage_1_steps=30, context=ctx_v)
-        lat_out, _ = bank.get_ordered()
-        lat_host = lat_out.cpu()
-        torch.cuda.synchronize()
-        t2 = time.perf_counter()
-        video = {"sec_per_video_stage1": t2 - t0, "dinov2_encode_s": t1 - t0, "denoise_30_steps_s": t2 - t1,
-                 "frames": T, "steps": 30, "finite": bool(torch.isfinite(lat_host).all()),
-                 "note": "Stage-I path only (uint8 frames -> CUDA BitImageProcessor-equivalent preprocessing -> DinoV2 + 1 window x 30 steps, CFG 7.5) through "
-                         "Stage1Pipeline; Stage 0 (TripoSG) is out of scope and not included; Stage II is timed separately below"}
-        del enc, pipe
-        # Stage II on the same window: 16-block trunk re-run for each of the 15 target times + the
-        # fp32-grade vertex-query block for V = 20 000 anchor vertices (+ normals), B200Autoencoder.forward, host in/out.
-        from actionmesh_b200.autoencoder import B200Autoencoder
+            enc = B200ImageEncoder().to(dev)
+            enc.init_random_(seed=1235)  # DinoV2-L/14 shape, seeded random weights (no checkpoints offline)
+            rng = np.random.default_rng(7)
+            frames = [Image.fromarray(rng.integers(0, 255, (512, 512, 3), dtype=np.uint8), "RGB") for _ in range(T)]
+            pipe = Stage1Pipeline(model, B200SchedulerFlow(num_inference_steps=30, shift=3.0, is_additive=True), cf, enc)
+            anchor = torch.randn(1, N, C, generator=torch.Generator().manual_seed(99))
+            vin = VideoInput(frames, torch.arange(T, dtype=torch.float32))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx_v = pipe.encode_all_frames(vin)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            bank = pipe(vin, anchor, seed=44, stage_1_steps=30, context=ctx_v)
+            lat_out, _ = bank.get_ordered()
+            lat_host = lat_out.cpu()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            video = {"sec_per_video_stage1": t2 - t0, "dinov2_encode_s": t1 - t0, "denoise_30_steps_s": t2 - t1,
+                     "frames": T, "steps": 30, "finite": bool(torch.isfinite(lat_host).all()),
+                     "note": "Stage-I path only (uint8 frames -> CUDA BitImageProcessor-equivalent preprocessing -> DinoV2 + 1 window x 30 steps, CFG 7.5) through "
+                             "Stage1Pipeline; Stage 0 (TripoSG) is out of scope and not included; Stage II is timed separately below"}
+            del enc, pipe
+            # Stage II on the same window: 16-block trunk re-run for each of the 15 target times + the
+            # fp32-grade vertex-query block for V = 20 000 anchor vertices (+ normals), B200Autoencoder.forward, host in/out.
+            from actionmesh_b200.autoencoder import B200Autoencoder
 
-        ae = B200Autoencoder().to(dev)
-        ae.init_random_(seed=1236)
-        gq = torch.Generator().manual_seed(13)
-        pts = torch.randn(1, 20000, 3, generator=gq)
-        pts = pts / pts.norm(dim=-1, keepdim=True) * 0.6
-        query = torch.cat([pts, pts / 0.6], dim=-1)
-        tgt = torch.linspace(0, 1, T)[None, 1:]
-        ae.forward(lat_host[None, :3], torch.arange(3.0)[None], torch.zeros(1), tgt[:, :1], query[:, :512])  # warm-up
-        ops.event_log, ops.event_tags = [], {"s2_attn", "s2_gemm", "s2_q"}
-        torch.cuda.synchronize()
-        t3 = time.perf_counter()
-        disp = ae.forward(lat_host[None], torch.arange(T, dtype=torch.float32)[None], torch.zeros(1), tgt, query)
-        verts = ae.apply_displacement(query[..., :3].to(dev), disp).cpu()
-        torch.cuda.synchronize()
-        t4 = time.perf_counter()
-        s2 = {}
-        for tag, e0, e1 in ops.event_log:
-            s2[tag] = s2.get(tag, 0.0) + e0.elapsed_time(e1)
-        ops.event_log = None
-        video.update({"stage2_decode_s": t4 - t3, "stage2_targets": int(tgt.shape[1]), "stage2_vertices": 20000,
-                      "stage2_kernel_ms": {"trunk_attention": s2.get("s2_attn"), "trunk_gemm": s2.get("s2_gemm"),
-                                           "query_path_gemm": s2.get("s2_q")},
-                      "stage2_finite": bool(torch.isfinite(verts).all()),
-                      "sec_per_video_stage1_plus_stage2": (t2 - t0) + (t4 - t3)})
-        del ae
+            ae = B200Autoencoder().to(dev)
+            ae.init_random_(seed=1236)
+            gq = torch.Generator().manual_seed(13)
+            pts = torch.randn(1, 20000, 3, generator=gq)
+            pts = pts / pts.norm(dim=-1, keepdim=True) * 0.6
+            query = torch.cat([pts, pts / 0.6], dim=-1)
+            tgt = torch.linspace(0, 1, T)[None, 1:]
+            ae.forward(lat_host[None, :3], torch.arange(3.0)[None], torch.zeros(1), tgt[:, :1], query[:, :512])  # warm-up
+            ops.event_log, ops.event_tags = [], {"s2_attn", "s2_gemm", "s2_q"}
+            torch.cuda.synchronize()
+            t3 = time.perf_counter()
+            disp = ae.forward(lat_host[None], torch.arange(T, dtype=torch.float32)[None], torch.zeros(1), tgt, query)
+            verts = ae.apply_displacement(query[..., :3].to(dev), disp).cpu()
+            torch.cuda.synchronize()
+            t4 = time.perf_counter()
+            s2 = {}
+            for tag, e0, e1 in ops.event_log:
+                s2[tag] = s2.get(tag, 0.0) + e0.elapsed_time(e1)
+            ops.event_log = None
+            video.update({"stage2_decode_s": t4 - t3, "stage2_targets": int(tgt.shape[1]), "stage2_vertices": 20000,
+                          "stage2_kernel_ms": {"trunk_attention": s2.get("s2_attn"), "trunk_gemm": s2.get("s2_gemm"),
+                                               "query_path_gemm": s2.get("s2_q")},
+                          "stage2_finite": bool(torch.isfinite(verts).all()),
+                          "sec_per_video_stage1_plus_stage2": (t2 - t0) + (t4 - t3)})
+            del ae
+        except Exception as exc:  # noqa: BLE001 - an optional leg must never cost the main JSON line
+            video = dict(video or {}, error=f"{type(exc).__name__}: {exc}"[:400])
 
     if rank != 0:
         if world > 1:
