@@ -106,3 +106,26 @@ def test_missing_library_raises(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.AmbError):
         _lib.load_library()
+
+
+def test_argument_validation_of_widened_entry_points(amb_lib):
+    """Stage-II helpers and the preprocessing kernels validate their geometry before any launch (fake non-null pointers)."""
+    P = 16
+    err = lambda: amb_lib.amb_last_error().decode()
+    assert amb_lib.amb_split3_bf16(None, 0, 1, 128, 128, 0, None, 0, None) < 0 and "null pointer" in err()
+    assert amb_lib.amb_split3_bf16(P, 128, 1, 128, 96, 0, P, 384, None) < 0 and "bad geometry" in err()     # cols % seg != 0
+    assert amb_lib.amb_split3_bf16(P, 128, 1, 128, 128, 0, P, 256, None) < 0 and "bad geometry" in err()    # ld_dst < 3*cols
+    assert amb_lib.amb_softmax_split3(P, 128, 1, 130, 128, 1.0, P, 384, None) < 0 and "bad geometry" in err()  # n > n_pad
+    assert amb_lib.amb_softmax_split3(P, 64, 1, 100, 128, 1.0, P, 384, None) < 0                               # ld_s < n_pad
+    assert amb_lib.amb_alpha_rows(0.0, 1.0, 511, P, 1024, 1, None) < 0 and "alpha_rows" in err()               # odd size
+    assert amb_lib.amb_point_embedding(P, 4, 6, 3, 8, 0, P, 32, None) < 0 and "bad geometry" in err()          # kpad too small
+    assert amb_lib.amb_point_embedding(P, 4, 5, 3, 8, 0, P, 64, None) < 0                                      # in_dim != 3 + extra
+    assert amb_lib.amb_displacement_out(P, 2, 4, 3, P, None) < 0                                               # ld < out_dim
+    assert amb_lib.amb_resize_h_u8(P, 1, 64, 64, 2, 0, 64, P, P, 9, 32, P, None) < 0 and "bad geometry" in err()  # 2 channels
+    assert amb_lib.amb_resize_h_u8(P, 1, 64, 64, 3, 60, 8, P, P, 9, 32, P, None) < 0 and "outside the image" in err()
+    m = (C.c_float * 3)(0, 0, 0)
+    assert amb_lib.amb_resize_v_normalize(P, 1, 0, 0, 32, P, P, 9, 32, P, m, m, P, None, None) < 0 and "bad geometry" in err()
+    assert amb_lib.amb_resize_v_normalize(P, 1, 8, 0, 32, P, P, 9, 32, None, m, m, P, None, None) < 0 and "null pointer" in err()
+    # zero-size work is a successful no-op without a launch
+    assert amb_lib.amb_split3_bf16(P, 128, 0, 128, 128, 0, P, 384, None) == 0
+    assert amb_lib.amb_resize_h_u8(P, 0, 64, 64, 3, 0, 64, P, P, 9, 32, P, None) == 0
