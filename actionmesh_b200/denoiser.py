@@ -175,10 +175,15 @@ class B200Denoiser:
                 h_in = h
             ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
             if i in c.inflated_layers:
-                ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
+                peer = ws.get("peer_gather")  # experimental copy-engine gather over NVLink peer memory (window_shard.PeerGather)
+                kv_out = kv_local if peer is None else peer.local(b, i & 1)
+                ops.gemm(xn, w[p + "s.qkv"][D:], kv_out,
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
                                    rows_per_pos=L))
-                work = dist.all_gather_into_tensor(kv_all.view(-1, 2 * D), kv_local, group=shard.group, async_op=True)
+                if peer is None:
+                    work = dist.all_gather_into_tensor(kv_all.view(-1, 2 * D), kv_local, group=shard.group, async_op=True)
+                else:
+                    work = peer.gather(b, i & 1, kv_all)
                 ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
                                    rows_per_pos=L))
@@ -421,6 +426,10 @@ class B200Denoiser:
         ops.gemm(ws["t_hid"], w["time2.w"], h, bias=w["time2.b"], row_map=(1, L, 0))
 
         if shard is not None and shard.world > 1:
+            if os.environ.get("AMB_SHARD_P2P", "0") == "1" and "peer_gather" not in ws:
+                from .window_shard import PeerGather
+
+                ws["peer_gather"] = PeerGather(shard, B, T * L, 2 * D, self._device)
             # frame-sharded window: the CFG branches are independent through the whole network, so they run as staggered
             # programs on the one compute stream — while branch b's K/V all-gather is in flight the other branch runs its
             # attention / MLP (see _branch_program).  Everything below this block is the single-GPU path.

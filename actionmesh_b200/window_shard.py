@@ -55,6 +55,60 @@ def configure_nccl_env() -> None:
     os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
 
 
+class _EventWork:
+    """`.wait()` with the semantics of an async NCCL work handle: the CURRENT stream waits for the recorded event."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
+class PeerGather:
+    """EXPERIMENTAL (off by default, `AMB_SHARD_P2P=1`; written at the end of round 1 and NOT yet run on hardware):
+    the per-layer K/V all-gather over NVLink peer memory with the COPY ENGINES instead of an NCCL kernel.
+
+    Why: the timeline of the 8-GPU sharded window (profiles/r01_shard_profile_8gpu.log) shows that what the all-gather
+    costs is not its latency but its SMs — the NCCL kernel (32 channels) runs next to persistent GEMMs / multi-wave
+    attention and inflates their time by ~12 ms per step.  DMA copies take no SM.
+
+    How: every rank's K/V projection writes into a symmetric-memory buffer (torch.distributed._symmetric_memory, one
+    allocation per rank, mapped into every peer).  `gather()` then, on a side stream: device-side barrier across ranks
+    (all projections of this layer/branch are complete) -> `world` contiguous peer->local copies (cudaMemcpyAsync D2D,
+    starting with the local chunk, peers visited in a rank-rotated order so each NVLink port sees one reader at a time)
+    -> event.  The buffer is double-buffered by layer parity: a rank overwrites parity p again two layers later, after it
+    passed the barrier of the layer in between, which every peer enters only after its own copies of this layer."""
+
+    def __init__(self, shard: "FrameShard", branches: int, rows: int, cols: int, device: torch.device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.world, self.rank = shard.world, shard.rank
+        group = shard.group if shard.group is not None else dist.group.WORLD
+        self.buf = symm_mem.empty((2, branches, rows, cols), dtype=torch.bfloat16, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        shape = (2, branches, rows, cols)
+        self.peers = [self.buf if r == self.rank else self.hdl.get_buffer(r, shape, torch.bfloat16) for r in range(self.world)]
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+
+    def local(self, branch: int, parity: int) -> torch.Tensor:
+        return self.buf[parity, branch]
+
+    def gather(self, branch: int, parity: int, kv_all_b: torch.Tensor) -> _EventWork:
+        """kv_all_b (world, rows, cols) <- every rank's local(branch, parity); asynchronous w.r.t. the current stream."""
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            self.hdl.barrier(channel=branch)
+            for k in range(self.world):
+                r = (self.rank + k) % self.world
+                kv_all_b[r].copy_(self.peers[r][parity, branch], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return _EventWork(done)
+
+
 class FrameShard:
     """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed."""
 

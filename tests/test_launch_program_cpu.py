@@ -135,3 +135,51 @@ def test_sharded_branch_programs_interleave(monkeypatch):
             assert not (tags[i + 1][0] == "wait" and tags[i + 1][1] == tags[i][1]), "a gather was waited on immediately"
     attn = [c for c in rec.calls if c[0] == "attn_self"]
     assert len(attn) == B * cfg.num_layers and all(c[1] == (1, T * (N + 1), 2, 128) and c[2][:3] == (1, world, T * (N + 1)) for c in attn)
+
+
+def test_sharded_program_with_peer_gather_plumbing(monkeypatch):
+    """AMB_SHARD_P2P=1: the K/V projection writes into the (double-buffered) symmetric buffer and the gather handle is waited
+    on before attention; checked with a fake PeerGather (the real one needs CUDA symmetric memory)."""
+    from actionmesh_b200 import window_shard
+
+    m, rec, cfg = _model(monkeypatch)
+    log = []
+
+    class FakePeer:
+        def __init__(self, shard, branches, rows, cols, device):
+            self.buf = torch.empty(2, branches, rows, cols, dtype=torch.bfloat16)
+            log.append(("init", branches, rows, cols))
+
+        def local(self, b, parity):
+            return self.buf[parity, b]
+
+        def gather(self, b, parity, kv_all_b):
+            assert kv_all_b.shape[1:] == self.buf.shape[2:]
+            log.append(("gather", b, parity))
+
+            class W:
+                def wait(self_inner):
+                    log.append(("wait", b, parity))
+
+            return W()
+
+    monkeypatch.setattr(window_shard, "PeerGather", FakePeer)
+    monkeypatch.setenv("AMB_SHARD_P2P", "1")
+    world, B, T_all, N = 2, 2, 4, 31
+    T = T_all // world
+
+    class Shard:
+        group = None
+
+    Shard.world, Shard.rank = world, 0
+    ctx = torch.randn(B, T_all, 9, 128)
+    fs = torch.arange(T_all, dtype=torch.float32)[None].repeat(B, 1)
+    st = m.precompute_window(ctx, fs, N, frame_slice=slice(0, T))
+    ws = m._workspace(B, T, N, world=world)
+    m._forward_packed(ws, st, B, T, N, torch.tensor([500.0]), None, n_input_branches=2, shard=Shard)
+    m._forward_packed(ws, st, B, T, N, torch.tensor([400.0]), None, n_input_branches=2, shard=Shard)   # buffer reused, one init
+    assert [e for e in log if e[0] == "init"] == [("init", B, T * (N + 1), 2 * cfg.width)]
+    g = [e for e in log if e[0] == "gather"]
+    assert len(g) == 2 * B * cfg.num_layers
+    assert [e[2] for e in g[:2 * B]] == [0, 0, 1, 1]                      # parity alternates by layer, both branches per layer
+    assert len([e for e in log if e[0] == "wait"]) == len(g)
