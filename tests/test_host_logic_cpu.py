@@ -1,7 +1,9 @@
 """Host-side mirror of the reference interfaces (no GPU): schedule, CFG, weight re-packing, windows."""
 import torch
 
-from conftest import load_golden
+import os
+
+from conftest import ROOT, load_golden
 from actionmesh_b200.denoiser import repack_cross_kv, repack_self_qkv
 from actionmesh_b200.guidance import ClassifierFreeGuidance
 from actionmesh_b200.scheduler import B200SchedulerFlow
@@ -76,3 +78,28 @@ def test_windows_and_bank_match_reference_known_answers():
     bank.update(torch.tensor([1.0]), torch.full((1, 4, 2), 2.0))
     lat, ts = bank.get_ordered()
     assert ts.tolist() == [1.0, 3.0] and float(lat[0, 0, 0]) == 2.0
+
+
+def test_exp2_emulation_polynomial_error_bound():
+    """The attention kernel evaluates a fraction of its exponentials with a cubic on the FMA pipe (csrc/ptx.cuh exp2_poly2).
+    Re-evaluate that polynomial (constants parsed from the source, fp32 Horner in the kernel's order, including the
+    round-to-nearest range reduction and the exponent patch) against 2^x: max relative error < 1e-4, |mean| < 1e-5."""
+    import re
+
+    import numpy as np
+
+    src = open(os.path.join(ROOT, "actionmesh_b200", "csrc", "ptx.cuh")).read()
+    c = {k: np.float32(v) for k, v in re.findall(r"kExp2(C[0-3]) = ([0-9.]+)f", src)}
+    assert sorted(c) == ["C0", "C1", "C2", "C3"]
+    x = np.linspace(-40.0, 0.0, 4_000_001).astype(np.float32)
+    magic = np.float32(12582912.0)
+    t = x + magic
+    n = t - magic
+    f = (n * np.float32(-1.0) + x).astype(np.float32)
+    assert np.abs(f).max() <= 0.5
+    p = (f * c["C3"] + c["C2"]).astype(np.float32)
+    p = (p * f + c["C1"]).astype(np.float32)
+    p = (p * f + c["C0"]).astype(np.float32)
+    e = (p.view(np.uint32) + (t.view(np.uint32) << np.uint32(23))).view(np.float32)
+    rel = (e.astype(np.float64) - 2.0 ** x.astype(np.float64)) / 2.0 ** x.astype(np.float64)
+    assert np.abs(rel).max() < 1e-4 and abs(rel.mean()) < 1e-5, (np.abs(rel).max(), rel.mean())
