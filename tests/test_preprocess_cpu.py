@@ -73,3 +73,30 @@ def test_preprocessor_refuses_cpu():
 
     with pytest.raises(AmbError):
         pp.B200ImagePreprocessor().preprocess_u8(torch.zeros(1, 32, 32, 3, dtype=torch.uint8), "cpu")
+
+
+def test_random_sizes_against_pillow_property():
+    """Property test over random (in, out) sizes incl. up-scaling, extreme aspect ratios and tiny images: the product table
+    driven through the integer convolution equals Pillow on one axis (a 1-row / 1-column strip keeps it fast)."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n_in=st.integers(2, 1500), n_out=st.integers(2, 700), seed=st.integers(0, 2 ** 16))
+    def check(n_in, n_out, seed):
+        rng = np.random.default_rng(seed)
+        strip = rng.integers(0, 256, (3, n_in, 3), dtype=np.uint8)            # 3 rows, n_in columns
+        ref = np.asarray(Image.fromarray(strip, "RGB").resize((n_out, 3), resample=Image.BICUBIC))
+        if n_in == n_out:
+            assert np.array_equal(ref, strip)
+            return
+        b, k = pp.resample_table(n_in, n_out)
+        x = strip.astype(np.int64)
+        out = np.empty((3, n_out, 3), dtype=np.int64)
+        for j in range(n_out):
+            xmin, n = b[j]
+            acc = (1 << 21) + (x[:, xmin:xmin + n] * k[j, :n].astype(np.int64)[None, :, None]).sum(1)
+            out[:, j] = np.clip(acc >> 22, 0, 255)
+        assert np.array_equal(out.astype(np.uint8), ref), (n_in, n_out)
+
+    check()
