@@ -100,3 +100,28 @@ def test_random_sizes_against_pillow_property():
         assert np.array_equal(out.astype(np.uint8), ref), (n_in, n_out)
 
     check()
+
+
+def test_c_oracle_is_bit_exact_vs_pillow():
+    """oracle/pil_resample.c (plain-C restatement of Pillow's Resample.c, built by __graft_entry__.build()) against Pillow."""
+    import ctypes
+    import os
+    import subprocess
+
+    from conftest import ROOT
+
+    so = os.path.join(ROOT, "oracle", "_build", "libpil_resample.so")
+    if not os.path.exists(so):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    lib = ctypes.CDLL(so)
+    lib.amb_oracle_resize_u8.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_void_p]
+    rng = np.random.default_rng(11)
+    for (h, w, oh, ow, c) in [(512, 512, 256, 256, 3), (300, 400, 256, 341, 3), (96, 130, 256, 346, 3), (256, 300, 256, 300, 3),
+                              (257, 256, 257, 256, 3), (720, 405, 455, 256, 3)]:   # RGB only: PIL premultiplies RGBA; the
+                                                                                  # pipeline converts to RGB first
+        a = np.ascontiguousarray(rng.integers(0, 256, (h, w, c), dtype=np.uint8))
+        out = np.empty((oh, ow, c), dtype=np.uint8)
+        assert lib.amb_oracle_resize_u8(a.ctypes.data, h, w, c, oh, ow, out.ctypes.data) == 0
+        ref = np.asarray(Image.fromarray(a, "RGB").resize((ow, oh), resample=Image.BICUBIC))
+        assert np.array_equal(out, ref), (h, w, oh, ow, c)
