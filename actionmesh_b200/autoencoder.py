@@ -116,6 +116,7 @@ class B200Autoencoder:
         model.load_state_dict(sd)
         return model
 
+    @ops.on_device
     def load_state_dict(self, sd: dict) -> None:
         """Pack the reference's state dict: trunk GEMM weights bf16 (QKV fused + head-permuted); the fp32 query-path
         weights as split-bf16 [hi | hi | lo] operands; biases / norm weights fp32."""
@@ -173,6 +174,7 @@ class B200Autoencoder:
         self._w = w
         self._loaded = True
 
+    @ops.on_device
     def init_random_(self, seed: int = 1236) -> None:
         """Synthetic weights for benchmarks (no checkpoints offline): torch default Linear/LayerNorm inits, residual-branch
         output projections scaled by 1/sqrt(num_layers + 1), generated on the GPU."""
@@ -222,6 +224,7 @@ class B200Autoencoder:
     def __call__(self, *args, **kwargs):
         return self.forward(*args, **kwargs)
 
+    @ops.on_device
     @torch.no_grad()
     def forward(self, latent: torch.Tensor, framestep: torch.Tensor, source_alpha: torch.Tensor,
                 target_alphas: torch.Tensor, query: torch.Tensor,

@@ -1,5 +1,6 @@
 // C-ABI plumbing: last-error buffer, tensor-map encoder, device query.
 #include <cstdarg>
+#include <mutex>
 #include "common.cuh"
 #include "../../include/actionmesh_b200.h"
 
@@ -62,15 +63,36 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   return AMB_OK;
 }
 
+// Per-(kernel, device) opt-in to > 48 KB of dynamic shared memory (the attribute is a per-device setting).
+int ensure_smem_optin_impl(const void* kern, int bytes) {
+  constexpr int MAXK = 64, MAXD = 16;
+  static const void* keys[MAXK] = {};
+  static bool done[MAXK][MAXD] = {};
+  static std::mutex mu;
+  int dev = 0;
+  AMB_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  int slot = -1;
+  for (int i = 0; i < MAXK; ++i) {
+    if (keys[i] == kern) { slot = i; break; }
+    if (keys[i] == nullptr) { keys[i] = kern; slot = i; break; }
+  }
+  if (slot >= 0 && dev < MAXD && done[slot][dev]) return AMB_OK;
+  AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (slot >= 0 && dev < MAXD) done[slot][dev] = true;
+  return AMB_OK;
+}
+
+// SM count of the CURRENT device (cached per device).
 int num_sms() {
-  static int n = 0;
-  if (n) return n;
+  static int n[16] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-  cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 148;
-  n = prop.multiProcessorCount;
-  return n;
+  if (dev < 16 && n[dev]) return n[dev];
+  int v = 0;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  if (dev < 16) n[dev] = v;
+  return v;
 }
 
 }  // namespace amb

@@ -14,7 +14,7 @@
 #include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
-#include "../../include/actionmesh_b200.h"
+#include "attention.cuh"
 
 namespace amb {
 
@@ -29,15 +29,6 @@ __device__ __forceinline__ void trace_ev(long long* tr, int role, int j, int ev)
 constexpr int ATT_BQ = 128;   // rows per query tile
 constexpr int ATT_BK = 64;    // keys per K/V tile
 constexpr int ATT_THREADS = 320;
-
-struct AttnParams {
-  __nv_bfloat16* o;
-  long long o_stride_b, o_stride_h, o_stride_s;
-  int heads, sq, sk;
-  int kv_chunks, sk_chunk;   // kv split into chunks along the outermost tensor-map coordinate
-  float scale_log2;          // scale * log2(e)
-  long long* trace;          // optional device buffer for the clock64 timeline of CTA (0,0,0) (debug; NULL = off)
-};
 
 template <int D, int STAGES>
 struct AttnSmem {
@@ -701,416 +692,34 @@ flash_attn_fwd_v4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
 }
 
 
-// =====================================================================================================================
-// v5 (head_dim 128): P no longer aliases S.  With 80-key tiles the TMEM budget is S 2x80 + P 2x40 + O 2x128 = 496
-// columns, so the QK^T of key tile j+1 is issued as soon as the softmax threads have READ S_j (not after P_j·V_j), and
-// P_j·V_j leaves the QK^T -> softmax -> QK^T critical path entirely: the tensor pipe runs one S tile ahead per query tile
-// while the softmax warps never wait on it.  Two threads per query row as in v4 (16 softmax warps, 40 keys each).
-//   TMEM: S[i] = 80 i, P[i] = 160 + 40 i, O[i] = 256 + 128 i.     Tensor-pipe order: S0 S1 | S0' S1' PV0 PV1 | ...
-// =====================================================================================================================
-constexpr int V5_BK = 80;
-
-template <int KSTAGES, int VSTAGES>
-struct AttnV5Smem {
-  static constexpr int Q_TILE_BYTES = 128 * 128 * 2;
-  static constexpr int KV_HALF_BYTES = V5_BK * 128;          // one 64-column half of a K/V tile: 10 swizzle atoms
-  static constexpr int KV_TILE_BYTES = 2 * KV_HALF_BYTES;    // 20 KB
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = 2 * Q_TILE_BYTES;
-  static constexpr int V_OFF = K_OFF + KSTAGES * KV_TILE_BYTES;
-  static constexpr int XCH_OFF = V_OFF + VSTAGES * KV_TILE_BYTES;
-  static constexpr int BAR_OFF = XCH_OFF + 2 * 2 * 128 * 4;
-  static constexpr int NUM_BARS = 1 + 2 * KSTAGES + 2 * VSTAGES + 2 + 2 + 2 + 2 + 2;
-  static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
-};
-
-template <int KSTAGES, int VSTAGES, int EMU>
-__global__ void __launch_bounds__(V4_THREADS, 1)
-flash_attn_fwd_v5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                         const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using L = AttnV5Smem<KSTAGES, VSTAGES>;
-  constexpr int D = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* k_full = q_full + 1;
-  uint64_t* k_empty = k_full + KSTAGES;
-  uint64_t* v_full = k_empty + KSTAGES;
-  uint64_t* v_empty = v_full + VSTAGES;
-  uint64_t* s_full = v_empty + VSTAGES;  // [2] MMA -> softmax: S_i(j) complete
-  uint64_t* s_free = s_full + 2;         // [2] softmax -> MMA: S_i(j) has been read (256 arrivals)
-  uint64_t* p_ready = s_free + 2;        // [2] softmax -> MMA: P_i(j) written (256 arrivals)
-  uint64_t* pv_done = p_ready + 2;       // [2] MMA -> softmax: P_i(j)·V_j complete (P_i reusable, O_i quiescent)
-  uint64_t* o_full = pv_done + 2;        // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
-
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * ATT_BQ);
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int tiles_per_chunk = (p.sk_chunk + V5_BK - 1) / V5_BK;
-  const int n_kv = p.kv_chunks * tiles_per_chunk;
-
-  if (warp == 16 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
-  if (warp == 17) {
-    if (lane == 0) {
-      mbar_init(q_full, 1);
-      for (int s = 0; s < KSTAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
-      for (int s = 0; s < VSTAGES; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-      for (int i = 0; i < 2; ++i) {
-        mbar_init(&s_full[i], 1);
-        mbar_init(&s_free[i], 256);
-        mbar_init(&p_ready[i], 256);
-        mbar_init(&pv_done[i], 1);
-        mbar_init(&o_full[i], 1);
-      }
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 16) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * L::Q_TILE_BYTES);
-      for (int i = 0; i < 2; ++i)
-        for (int c = 0; c < 2; ++c)
-          tma_load_4d(smem + L::Q_OFF + i * L::Q_TILE_BYTES + c * 16384, &tmQ, q_full, c * 64, q0 + i * ATT_BQ, head,
-                      batch, kEvictFirst);
-    }
-    __syncwarp();
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      const int chunk = j / tiles_per_chunk;
-      const int key0 = (j - chunk * tiles_per_chunk) * V5_BK;
-      mbar_wait(&k_empty[ks], kph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&k_full[ks], L::KV_TILE_BYTES);
-        uint8_t* sk = smem + L::K_OFF + ks * L::KV_TILE_BYTES;
-        tma_load_5d(sk, &tmK, &k_full[ks], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sk + L::KV_HALF_BYTES, &tmK, &k_full[ks], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-      if (++ks == KSTAGES) { ks = 0; kph ^= 1; }
-      mbar_wait(&v_empty[vs], vph ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&v_full[vs], L::KV_TILE_BYTES);
-        uint8_t* sv = smem + L::V_OFF + vs * L::KV_TILE_BYTES;
-        tma_load_5d(sv, &tmV, &v_full[vs], 0, key0, head, batch, chunk, kEvictLast);
-        tma_load_5d(sv + L::KV_HALF_BYTES, &tmV, &v_full[vs], 64, key0, head, batch, chunk, kEvictLast);
-      }
-      __syncwarp();
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-    }
-  } else if (warp == 17) {
-    // ===================== MMA issuer =====================
-    constexpr uint32_t idesc_qk = make_idesc_bf16(ATT_BQ, V5_BK, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(ATT_BQ, D, 0, 1);
-    const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
-    const uint32_t sk_addr = smem_u32(smem + L::K_OFF);
-    const uint32_t sv_addr = smem_u32(smem + L::V_OFF);
-
-    auto issue_qk = [=](int i, int kstage) {
-      const uint64_t qd = make_desc_kmajor_sw128(sq_addr + i * L::Q_TILE_BYTES);
-      const uint64_t kd = make_desc_kmajor_sw128(sk_addr + kstage * L::KV_TILE_BYTES);
-      const uint32_t d = tmem_base + i * V5_BK;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < D / 16; ++k)
-          mma_ss(d, qd + ((k >> 2) * (16384 / 16) + (k & 3) * 2), kd + ((k >> 2) * (L::KV_HALF_BYTES / 16) + (k & 3) * 2),
-                 idesc_qk, k != 0);
-        tc_commit(&s_full[i]);
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [=](int i, int vstage, bool first_tile) {
-      const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::KV_TILE_BYTES, L::KV_HALF_BYTES);
-      const uint32_t d = tmem_base + 256 + i * 128;
-      const uint32_t pa = tmem_base + 160 + i * 40;
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < V5_BK / 16; ++k)
-          mma_ts(d, pa + k * 8, vd + 128 * k, idesc_pv, (!first_tile || k != 0) ? 1u : 0u);
-        tc_commit(&pv_done[i]);
-      }
-      __syncwarp();
-    };
-    auto commit = [=](uint64_t* bar) {
-      if (elect_one()) tc_commit(bar);
-      __syncwarp();
-    };
-
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    issue_qk(1, 0);
-    commit(&k_empty[0]);
-    int ks = 0, vs = 0;
-    uint32_t kph = 0, vph = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      int ks_next = ks + 1;
-      uint32_t kph_next = kph;
-      if (ks_next == KSTAGES) { ks_next = 0; kph_next ^= 1; }
-      const bool has_next = (j + 1 < n_kv);
-      const uint32_t par = j & 1;
-      // ---- QK^T of the next key tile as soon as S_i(j) has been read
-      if (has_next) {
-        mbar_wait(&k_full[ks_next], kph_next);
-        mbar_wait(&s_free[0], par);
-        tc_fence_after();
-        issue_qk(0, ks_next);
-        mbar_wait(&s_free[1], par);
-        tc_fence_after();
-        issue_qk(1, ks_next);
-        commit(&k_empty[ks_next]);
-      }
-      // ---- P·V of this key tile
-      mbar_wait(&v_full[vs], vph);
-      mbar_wait(&p_ready[0], par);
-      tc_fence_after();
-      issue_pv(0, vs, j == 0);
-      if (!has_next) commit(&o_full[0]);
-      mbar_wait(&p_ready[1], par);
-      tc_fence_after();
-      issue_pv(1, vs, j == 0);
-      commit(&v_empty[vs]);
-      if (!has_next) commit(&o_full[1]);
-      ks = ks_next;
-      kph = kph_next;
-      if (++vs == VSTAGES) { vs = 0; vph ^= 1; }
-    }
-  } else {
-    // ===================== softmax: 2 tiles x 2 key-halves x 4 lane quarters =====================
-    const int tile = warp >> 3;
-    const int half = (warp >> 2) & 1;
-    const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
-    const int q_row = q0 + tile * ATT_BQ + row_in_tile;
-    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + tile * V5_BK + half * 40 + lane_sel;       // my 40 score columns
-    const uint32_t p_addr = tmem_base + 160 + tile * 40 + half * 20 + lane_sel;    // my 20 packed-P columns
-    const uint32_t o_addr = tmem_base + 256 + tile * 128 + half * 64 + lane_sel;   // my 64 O columns
-    float* x_mine = xch + (tile * 2 + half) * 128 + row_in_tile;
-    const float* x_other = xch + (tile * 2 + (half ^ 1)) * 128 + row_in_tile;
-    const uint32_t bar_id = 1 + tile;
-
-    float m_used = -INFINITY;
-    float row_sum = 0.f;
-    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * V5_BK;
-
-    auto softmax_step = [&](int j, auto masked_tag) {
-      constexpr bool MASKED = decltype(masked_tag)::value;
-      mbar_wait(&s_full[tile], j & 1);
-      tc_fence_after();
-      float sc[40];
-      tmem_ld_x32f(s_addr, sc);
-      tmem_ld_x8f(s_addr + 32, sc + 32);
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(&s_free[tile]);  // S_i(j) is in registers: the tensor pipe may overwrite it with S_i(j+1)
-      if (MASKED) {
-#pragma unroll
-        for (int t = 0; t < 40; ++t)
-          if (half * 40 + t >= last_valid) sc[t] = -INFINITY;
-      }
-      float mx0 = fmaxf(sc[0], sc[1]), mx1 = fmaxf(sc[2], sc[3]);
-#pragma unroll
-      for (int t = 4; t < 40; t += 4) {
-        mx0 = fmaxf(mx0, fmaxf(sc[t], sc[t + 1]));
-        mx1 = fmaxf(mx1, fmaxf(sc[t + 2], sc[t + 3]));
-      }
-      const float mxp = fmaxf(mx0, mx1);
-      *x_mine = mxp;
-      named_bar_sync(bar_id, 256);
-      const float m_new = fmaxf(m_used, fmaxf(mxp, *x_other));
-      const bool need = (m_new - m_used) * p.scale_log2 > 8.0f;
-      // P_i and O_i are only touched once P_i(j-1)·V has completed
-      if (j > 0) {
-        mbar_wait(&pv_done[tile], (j - 1) & 1);
-        tc_fence_after();
-      }
-      if (j == 0) {
-        m_used = m_new;
-      } else if (__any_sync(0xffffffffu, need)) {
-        const float alpha = need ? ex2_approx((m_used - m_new) * p.scale_log2) : 1.0f;
-        if (need) {
-          m_used = m_new;
-          row_sum *= alpha;
-        }
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-          float ov[32];
-          tmem_ld_x32f(o_addr + c, ov);
-          tmem_wait_ld();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) ov[t] *= alpha;
-          tmem_st_x32f(o_addr + c, ov);
-        }
-        tmem_wait_st();
-        named_bar_sync(3 + tile * 4 + quarter, 64);  // my row-partner warp has rescaled its O columns too
-      }
-      const float mb = m_used * p.scale_log2;
-      const uint64_t scale2 = pk2(p.scale_log2, p.scale_log2), nmb2 = pk2(-mb, -mb);
-      uint64_t psum2 = pk2(0.f, 0.f), psum2b = pk2(0.f, 0.f);
-      uint32_t pk[20];
-#pragma unroll
-      for (int t = 0; t < 40; t += 2) {
-        float x0, x1, e0, e1;
-        upk2(fma2(pk2(sc[t], sc[t + 1]), scale2, nmb2), x0, x1);
-        if (EMU > 0 && ((t >> 1) % (EMU > 0 ? EMU : 1)) == EMU - 1) {
-          exp2_poly2(x0, x1, e0, e1);
-        } else {
-          e0 = ex2_approx(x0);  // exp2(-inf) = 0 masks the tail
-          e1 = ex2_approx(x1);
-        }
-        if ((t >> 1) & 1) psum2b = add2(psum2b, pk2(e0, e1));
-        else psum2 = add2(psum2, pk2(e0, e1));
-        pk[t >> 1] = pack_bf16(e0, e1);
-      }
-      tmem_st_x16(p_addr, pk);
-      tmem_st_x4(p_addr + 16, pk + 16);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_ready[tile]);
-      {
-        float s0, s1;
-        upk2(add2(psum2, psum2b), s0, s1);
-        row_sum += s0 + s1;
-      }
-    };
-
-    const bool has_tail = last_valid < V5_BK;
-    int jj = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      const bool tail = has_tail && (jj == tiles_per_chunk - 1);
-      if (++jj == tiles_per_chunk) jj = 0;
-      if (tail) softmax_step(j, std::true_type{});
-      else softmax_step(j, std::false_type{});
-    }
-
-    // ---- epilogue
-    mbar_wait(&o_full[tile], 0);
-    tc_fence_after();
-    named_bar_sync(bar_id, 256);
-    *x_mine = row_sum;
-    named_bar_sync(bar_id, 256);
-    const float inv = 1.0f / (row_sum + *x_other);
-    __nv_bfloat16* orow = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h +
-                          (long long)q_row * p.o_stride_s + half * 64;
-#pragma unroll 1
-    for (int c = 0; c < 64; c += 32) {
-      float ov[32];
-      tmem_ld_x32f(o_addr + c, ov);
-      tmem_wait_ld();
-      if (q_row < p.sq) {
-#pragma unroll
-        for (int t = 0; t < 32; t += 8) {
-          uint4 pk;
-          pk.x = pack_bf16(ov[t] * inv, ov[t + 1] * inv);
-          pk.y = pack_bf16(ov[t + 2] * inv, ov[t + 3] * inv);
-          pk.z = pack_bf16(ov[t + 4] * inv, ov[t + 5] * inv);
-          pk.w = pack_bf16(ov[t + 6] * inv, ov[t + 7] * inv);
-          *reinterpret_cast<uint4*>(orow + c + t) = pk;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 17) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
+template <int D, int STAGES>  // baseline single-CTA kernel (head_dim 64: DinoV2's attention)
+static int launch_attn_v1(const amb_attn_args* a, cudaStream_t stream) {
+  using L = AttnSmem<D, STAGES>;
+  CUtensorMap tmQ, tmK, tmV;
+  int r = encode_attn_maps(a, D, ATT_BQ, ATT_BK, ATT_BK, &tmQ, &tmK, &tmV);
+  if (r) return r;
+  const AttnParams p = make_attn_params(a, g_attn_trace);
+  dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
+  auto kern = flash_attn_fwd_kernel<D, STAGES>;
+  r = ensure_smem_optin(kern, L::TOTAL);
+  if (r) return r;
+  kern<<<grid, ATT_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
 }
 
-template <int D, int STAGES, int VER>  // VER: 1 = baseline kernel (head_dim 64 or 128), 4 = product kernel, 5 = 80-key variant (head_dim 128)
-static int launch_attn(const amb_attn_args* a, cudaStream_t stream) {
-  using L = AttnSmem<D, STAGES>;
+// single-CTA head_dim-128 kernel (two 128-row query tiles per CTA)
+static int launch_attn_v4(const amb_attn_args* a, cudaStream_t stream) {
   using L4 = AttnV4Smem<2, 2>;
-  using L5 = AttnV5Smem<3, 3>;
-  constexpr int BKV = (VER == 4) ? V2_BK : (VER == 5) ? V5_BK : ATT_BK;
   CUtensorMap tmQ, tmK, tmV;
-  const int chunks = a->kv_chunks > 0 ? a->kv_chunks : 1;
-  const int sk_chunk = chunks > 1 ? a->sk_chunk : a->sk;
-  {
-    uint64_t dims[4] = {(uint64_t)D, (uint64_t)a->sq, (uint64_t)a->heads, (uint64_t)a->batch};
-    uint64_t str[3] = {(uint64_t)a->q_stride_s * 2, (uint64_t)a->q_stride_h * 2, (uint64_t)a->q_stride_b * 2};
-    uint32_t box[4] = {64, ATT_BQ, 1, 1};
-    int r = encode_tmap_bf16(&tmQ, a->q, 4, dims, str, box);
-    if (r) return r;
-  }
-  // K/V maps are 5-D (d, key, head, batch, chunk) with free strides: one chunk per rank of a frame-sharded window
-  // (all-gather output is chunk-major), a single chunk otherwise.
-  auto enc_kv = [&](CUtensorMap* tm, const void* base, int64_t ss, int64_t sh, int64_t sb, int64_t schunk) -> int {
-    if (chunks == 1) schunk = sb > 0 ? sb : 16;  // extent-1 dimension: any legal stride
-    uint64_t dims[5] = {(uint64_t)D, (uint64_t)sk_chunk, (uint64_t)a->heads, (uint64_t)a->batch, (uint64_t)chunks};
-    uint64_t str[4] = {(uint64_t)ss * 2, (uint64_t)sh * 2, (uint64_t)sb * 2, (uint64_t)schunk * 2};
-    if (a->batch == 1 && str[2] == 0) str[2] = str[0] * sk_chunk;
-    uint32_t box[5] = {64, BKV, 1, 1, 1};
-    return encode_tmap_bf16(tm, base, 5, dims, str, box);
-  };
-  int r = enc_kv(&tmK, a->k, a->k_stride_s, a->k_stride_h, a->k_stride_b, a->k_chunk_stride);
+  int r = encode_attn_maps(a, 128, ATT_BQ, V2_BK, V2_BK, &tmQ, &tmK, &tmV);
   if (r) return r;
-  r = enc_kv(&tmV, a->v, a->v_stride_s, a->v_stride_h, a->v_stride_b, a->v_chunk_stride);
-  if (r) return r;
-
-  AttnParams p;
-  p.o = reinterpret_cast<__nv_bfloat16*>(a->o);
-  p.o_stride_b = a->o_stride_b; p.o_stride_h = a->o_stride_h; p.o_stride_s = a->o_stride_s;
-  p.heads = a->heads; p.sq = a->sq; p.sk = a->sk;
-  p.kv_chunks = chunks; p.sk_chunk = sk_chunk;
-  p.scale_log2 = a->scale * 1.4426950408889634f;
-  p.trace = g_attn_trace;
-
+  const AttnParams p = make_attn_params(a, g_attn_trace);
   dim3 grid((a->sq + 2 * ATT_BQ - 1) / (2 * ATT_BQ), a->heads, a->batch);
-  static bool attr_set = false;
-  if constexpr (VER == 5) {
-    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
-    auto kern = emu == 0 ? flash_attn_fwd_v5_kernel<3, 3, 0>
-              : emu == 2 ? flash_attn_fwd_v5_kernel<3, 3, 2>
-                         : flash_attn_fwd_v5_kernel<3, 3, 4>;
-    if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v5_kernel<3, 3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L5::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v5_kernel<3, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L5::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v5_kernel<3, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L5::TOTAL));
-      attr_set = true;
-    }
-    kern<<<grid, V4_THREADS, L5::TOTAL, stream>>>(tmQ, tmK, tmV, p);
-  } else if constexpr (VER == 4) {
-    static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 4; }();
-    auto kern = emu == 0 ? flash_attn_fwd_v4_kernel<2, 2, 0>
-              : emu == 2 ? flash_attn_fwd_v4_kernel<2, 2, 2>
-                         : flash_attn_fwd_v4_kernel<2, 2, 4>;
-    if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_fwd_v4_kernel<2, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L4::TOTAL));
-      attr_set = true;
-    }
-    kern<<<grid, V4_THREADS, L4::TOTAL, stream>>>(tmQ, tmK, tmV, p);
-  } else {
-    auto kern = flash_attn_fwd_kernel<D, STAGES>;
-    if (!attr_set) {
-      AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-      attr_set = true;
-    }
-    kern<<<grid, ATT_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
-  }
+  auto kern = flash_attn_fwd_v4_kernel<2, 2, 4>;
+  r = ensure_smem_optin(kern, L4::TOTAL);
+  if (r) return r;
+  kern<<<grid, V4_THREADS, L4::TOTAL, stream>>>(tmQ, tmK, tmV, p);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }
@@ -1137,11 +746,9 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
                 "flash_attn: kv_chunks * sk_chunk must equal sk");
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
-  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 4; }();  // 4 = product kernel; 1 and 5 kept for A/B
-  if (a->head_dim == 128) {
-    if (ver == 1) return launch_attn<128, 3, 1>(a, s);
-    if (ver == 5) return launch_attn<128, 3, 5>(a, s);
-    return launch_attn<128, 3, 4>(a, s);
-  }
-  return launch_attn<64, 4, 1>(a, s);
+  if (a->head_dim == 64) return launch_attn_v1<64, 4>(a, s);
+  // development switch (A/B against the previous product kernel); the pair kernel is the product path
+  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 6; }();
+  if (ver == 4) return launch_attn_v4(a, s);
+  return launch_attn_pair(a, g_attn_trace, s);
 }

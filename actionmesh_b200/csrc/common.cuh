@@ -36,5 +36,11 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint32_t* box);
 
 int num_sms();
+int ensure_smem_optin_impl(const void* kern, int bytes);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-device setting: remembered per (kernel, device).
+template <typename Kern>
+inline int ensure_smem_optin(Kern kern, int bytes) {
+  return ensure_smem_optin_impl(reinterpret_cast<const void*>(kern), bytes);
+}
 
 }  // namespace amb

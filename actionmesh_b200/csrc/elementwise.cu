@@ -190,6 +190,21 @@ __global__ void __launch_bounds__(256) add_bias_rows_kernel(__nv_bfloat16* __res
   }
 }
 
+__global__ void __launch_bounds__(256) add_bias_rows_f32_kernel(float* __restrict__ y, long long ldy,
+                                                                const float* __restrict__ bias, long long rows, int cols) {
+  const int vec_per_row = cols >> 2;
+  const long long total = rows * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec_per_row;
+    const int c = (int)(i - r * vec_per_row) << 2;
+    float4* p = reinterpret_cast<float4*>(y + r * ldy + c);
+    float4 v = *p;
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + c));
+    v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    *p = v;
+  }
+}
+
 // DinoV2 patch embedding as a GEMM: im2col of (T,3,H,W) fp32 pixels into bf16 rows (t, py, px) x cols (c, ky, kx),
 // zero-padded from 3*P*P to `kpad` columns (HF Dinov2PatchEmbeddings is Conv2d(3, D, P, stride P)).
 __global__ void __launch_bounds__(256) patchify_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out,
@@ -510,12 +525,16 @@ int amb_timestep_embedding(const float* t, int n_t, const float* mask, int rows,
   return AMB_OK;
 }
 
-int amb_add_bias_rows(void* y_bf16, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream) {
-  AMB_CHECK_ARG(y_bf16 && bias, "add_bias_rows: null pointer");
+int amb_add_bias_rows(void* y, int y_fp32, int64_t ldy, const float* bias, int64_t rows, int cols, amb_stream_t stream) {
+  AMB_CHECK_ARG(y && bias, "add_bias_rows: null pointer");
   AMB_CHECK_ARG(cols % 8 == 0 && ldy % 8 == 0, "add_bias_rows: cols/ldy must be multiples of 8");
   if (rows <= 0) return AMB_OK;
-  add_bias_rows_kernel<<<grid_for(rows * (cols >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<__nv_bfloat16*>(y_bf16), ldy, bias, rows, cols);
+  if (y_fp32)
+    add_bias_rows_f32_kernel<<<grid_for(rows * (cols >> 2), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float*>(y), ldy, bias, rows, cols);
+  else
+    add_bias_rows_kernel<<<grid_for(rows * (cols >> 3), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__nv_bfloat16*>(y), ldy, bias, rows, cols);
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

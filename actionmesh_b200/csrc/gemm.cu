@@ -514,10 +514,9 @@ static int launch_gemm2(const amb_gemm_args* a, cudaStream_t stream) {
   }
   GemmParams p = make_params(a);
   auto kern = gemm2_bf16_kernel<STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
+  {
+    int r = ensure_smem_optin(kern, L::TOTAL);
+    if (r) return r;
   }
   const int num_tiles = (a->n / 256) * ((a->m + 2 * BM - 1) / (2 * BM));
   int clusters = num_sms() / 2;
@@ -557,10 +556,9 @@ static int launch_gemm(const amb_gemm_args* a, cudaStream_t stream) {
   }
   GemmParams p = make_params(a);
   auto kern = gemm_bf16_kernel<BN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    AMB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    attr_set = true;
+  {
+    int r = ensure_smem_optin(kern, L::TOTAL);
+    if (r) return r;
   }
   const int num_tiles = (a->n / BN) * ((a->m + BM - 1) / BM);
   int grid = num_sms();

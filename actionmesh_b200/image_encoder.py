@@ -87,6 +87,7 @@ class B200ImageEncoder:
         return self
 
     # ---- weights (HF Dinov2Model state-dict keys)
+    @ops.on_device
     def load_state_dict(self, sd: dict) -> None:
         dev = self._device
         if dev.type != "cuda":
@@ -128,6 +129,7 @@ class B200ImageEncoder:
         self._w = w
         self._loaded = True
 
+    @ops.on_device
     def init_random_(self, seed: int = 1235) -> None:
         """Synthetic DinoV2 weights with the HF key names (benchmarks only; no checkpoints offline)."""
         dev = self._device
@@ -156,6 +158,7 @@ class B200ImageEncoder:
         self.load_state_dict(sd)
 
     # ---- encode
+    @ops.on_device
     @torch.no_grad()
     def encode_images(self, images: List) -> torch.Tensor:
         """images: list of T PIL images -> context (T, 257, 1024) fp32 (image_encoder.py:38-55)."""
@@ -165,6 +168,7 @@ class B200ImageEncoder:
             self._gpu_preprocess = B200ImagePreprocessor.from_hf(self.image_preprocess_dino)
         return self.encode_pixel_values(self._gpu_preprocess.preprocess(images, self._device))
 
+    @ops.on_device
     @torch.no_grad()
     def encode_pixel_values(self, pixel_values: torch.Tensor) -> torch.Tensor:
         """pixel_values (T,3,224,224) fp32 (host or device) -> last_hidden_state (T, 1+g*g, D) fp32."""

@@ -37,6 +37,22 @@ class _Timed:
             event_log.append((self.tag, self.e0, self.e1))
 
 
+def on_device(fn):
+    """Method decorator for the module-level entry points: makes `self.device` the current CUDA device for the call (the C
+    ABI launches on the current device and stream)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        dev = self.device
+        if dev.type != "cuda":
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -50,6 +66,12 @@ def _need(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
         raise _lib.AmbError(f"{name}: expected a CUDA tensor (there is no CPU fallback)")
     if t.dtype != dtype:
         raise _lib.AmbError(f"{name}: expected {dtype}, got {t.dtype}")
+    # the C ABI launches on the CURRENT device and stream: a tensor of another device would be an illegal access (or
+    # silent peer traffic).  The module-level entry points (B200Denoiser.forward, B200SchedulerFlow.denoise, ...) make
+    # their own device current; direct callers of ops must do the same.
+    if t.device.index != torch.cuda.current_device():
+        raise _lib.AmbError(f"{name}: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}"
+                            " (wrap the call in torch.cuda.device(tensor.device))")
 
 
 def cfg_euler_step(latents: torch.Tensor, pred: torch.Tensor, scales: list[float], dt_signed: float,
@@ -250,10 +272,13 @@ def timestep_embedding(t: torch.Tensor, channels: int, out: Optional[torch.Tenso
 
 def add_bias_rows(y: torch.Tensor, bias: torch.Tensor) -> None:
     global launch_count
-    _need(y, torch.bfloat16, "y")
+    if y.dtype not in (torch.bfloat16, torch.float32):
+        raise _lib.AmbError(f"add_bias_rows: unsupported dtype {y.dtype}")
+    _need(y, y.dtype, "y")
     _need(bias, torch.float32, "bias")
     assert y.dim() == 2 and y.stride(1) == 1
-    rc = _lib.load_library().amb_add_bias_rows(y.data_ptr(), y.stride(0), bias.data_ptr(), y.shape[0], y.shape[1], _stream())
+    rc = _lib.load_library().amb_add_bias_rows(y.data_ptr(), int(y.dtype == torch.float32), y.stride(0), bias.data_ptr(),
+                                               y.shape[0], y.shape[1], _stream())
     _lib.check(rc, "amb_add_bias_rows")
     launch_count += 1
 

@@ -93,6 +93,12 @@ class B200SchedulerFlow:
         model = diffusion_model
         if init_latent.dtype != torch.float32 or not init_latent.is_cuda:
             raise AmbError("init_latent must be an fp32 CUDA tensor")
+        if init_latent.device != model.device:
+            raise AmbError(f"init_latent lives on {init_latent.device}, the model on {model.device}")
+        with torch.cuda.device(init_latent.device):  # the C ABI launches on the current device
+            return self._denoise(model, cf_guidance, init_latent, context, mask, framestep, step_callback, shard)
+
+    def _denoise(self, model, cf_guidance, init_latent, context, mask, framestep, step_callback, shard):
         latents = init_latent if init_latent.is_contiguous() else init_latent.contiguous()
         if mask is not None and not bool((mask == 0).any()):  # scheduler.py:245 asserts this every step; once is enough
             raise AssertionError("No unobserved frames found")
@@ -121,7 +127,8 @@ class B200SchedulerFlow:
             mk = mask.to(device=dev, dtype=torch.float32).reshape(B, T)
             m32 = torch.cat([mk if ul else torch.zeros_like(mk) for _, ul in branches], dim=0).reshape(K * B * T).contiguous()
             upd = (mk.reshape(B * T) == 0).to(torch.uint8)
-        ws = model._workspace(K * B, T, N, world=shard.world if fsl is not None else 1)
+        ws = model._workspace(K * B, T, N, world=shard.world if fsl is not None else 1,
+                              slot=getattr(shard, "slot", 0) if fsl is not None else 0)
         L = N + 1
         sign = 1.0 if self.is_additive else -1.0
         t_dev = timesteps.to(dev)

@@ -55,65 +55,11 @@ def configure_nccl_env() -> None:
     os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
 
 
-class _EventWork:
-    """`.wait()` with the semantics of an async NCCL work handle: the CURRENT stream waits for the recorded event."""
-
-    def __init__(self, event):
-        self.event = event
-
-    def wait(self):
-        torch.cuda.current_stream().wait_event(self.event)
-
-
-class PeerGather:
-    """EXPERIMENTAL (off by default, `AMB_SHARD_P2P=1`; written at the end of round 1 and NOT yet run on hardware):
-    the per-layer K/V all-gather over NVLink peer memory with the COPY ENGINES instead of an NCCL kernel.
-
-    Why: the timeline of the 8-GPU sharded window (profiles/r01_shard_profile_8gpu.log) shows that what the all-gather
-    costs is not its latency but its SMs — the NCCL kernel (32 channels) runs next to persistent GEMMs / multi-wave
-    attention and inflates their time by ~12 ms per step.  DMA copies take no SM.
-
-    How: every rank's K/V projection writes into a symmetric-memory buffer (torch.distributed._symmetric_memory, one
-    allocation per rank, mapped into every peer).  `gather()` then, on a side stream: device-side barrier across ranks
-    (all projections of this layer/branch are complete) -> `world` contiguous peer->local copies (cudaMemcpyAsync D2D,
-    starting with the local chunk, peers visited in a rank-rotated order so each NVLink port sees one reader at a time)
-    -> event.  The buffer is double-buffered by layer parity: a rank overwrites parity p again two layers later, after it
-    passed the barrier of the layer in between, which every peer enters only after its own copies of this layer."""
-
-    def __init__(self, shard: "FrameShard", branches: int, rows: int, cols: int, device: torch.device):
-        import torch.distributed._symmetric_memory as symm_mem
-
-        self.world, self.rank = shard.world, shard.rank
-        group = shard.group if shard.group is not None else dist.group.WORLD
-        self.buf = symm_mem.empty((2, branches, rows, cols), dtype=torch.bfloat16, device=device)
-        self.hdl = symm_mem.rendezvous(self.buf, group)
-        shape = (2, branches, rows, cols)
-        self.peers = [self.buf if r == self.rank else self.hdl.get_buffer(r, shape, torch.bfloat16) for r in range(self.world)]
-        self.stream = torch.cuda.Stream(device=device, priority=-1)
-
-    def local(self, branch: int, parity: int) -> torch.Tensor:
-        return self.buf[parity, branch]
-
-    def gather(self, branch: int, parity: int, kv_all_b: torch.Tensor) -> _EventWork:
-        """kv_all_b (world, rows, cols) <- every rank's local(branch, parity); asynchronous w.r.t. the current stream."""
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream())
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(ready)
-            self.hdl.barrier(channel=branch)
-            for k in range(self.world):
-                r = (self.rank + k) % self.world
-                kv_all_b[r].copy_(self.peers[r][parity, branch], non_blocking=True)
-            done = torch.cuda.Event()
-            done.record(self.stream)
-        return _EventWork(done)
-
-
 class FrameShard:
     """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed."""
 
     def __init__(self, group=None):
-        if group is None and dist.get_backend() == "nccl" and os.environ.get("AMB_SHARD_HIPRI", "1") != "0":
+        if group is None and dist.get_backend() == "nccl":
             # dedicated communicator on a HIGH-PRIORITY stream: the per-layer K/V all-gather has to run concurrently with
             # compute kernels that fill every SM (persistent GEMMs, multi-wave attention); at normal priority its CTAs
             # queue behind the pending compute CTAs and the gather is effectively serialised.
@@ -126,68 +72,13 @@ class FrameShard:
     def frames(self, n_frames: int) -> slice:
         return frame_partition(n_frames, self.world, self.rank)
 
+    def all_gather_kv(self, out: torch.Tensor, local: torch.Tensor):
+        """Asynchronous all-gather of this rank's (rows, 2D) [K|V] of one layer/branch into `out` (world*rows, 2D),
+        rank-major; returns a handle whose `.wait()` makes the current stream wait for it."""
+        return dist.all_gather_into_tensor(out, local, group=self.group, async_op=True)
+
     def gather_latents(self, local: torch.Tensor) -> torch.Tensor:
         """(1, T_local, N, C) fp32 per rank -> (1, T, N, C) on every rank (once per window)."""
         out = torch.empty((self.world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out.view(-1, *local.shape[2:]), local[0].contiguous(), group=self.group)
         return out.reshape(1, -1, *local.shape[2:])
-
-
-def run_temporal_bench(args, rank: int, local: int, world: int):
-    """bench.py --mode temporal: ONE default window, frames sharded over `world` ranks (strong scaling)."""
-    import json
-
-    from . import ops
-    from .denoiser import B200Denoiser, DenoiserConfig
-    from .guidance import ClassifierFreeGuidance
-    from .scheduler import B200SchedulerFlow
-
-    dev = torch.device("cuda", local)
-    K, W = args.steps, max(args.warmup, 0)
-    T, N, C, S, Dc = 16, 2048, 64, 257, 1024
-    shard = FrameShard()
-    model = B200Denoiser(DenoiserConfig()).to(dev)
-    model.init_random_(seed=1234)  # same seed on every rank => replicated weights
-    cf = ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
-    g = torch.Generator(device="cpu").manual_seed(44)
-    lat = torch.randn(1, T, N, C, generator=g).to(dev)
-    ctx = torch.randn(1, T, S, Dc, generator=torch.Generator().manual_seed(5)).to(dev)
-    mask = torch.zeros(1, T, device=dev)
-    mask[0, 0] = 1.0
-    framestep = torch.arange(T, dtype=torch.float32)[None]
-    sch = B200SchedulerFlow(num_inference_steps=W + K, shift=3.0, is_additive=True)
-    ev = {}
-    marks = {"l0": 0}
-
-    def cb(step, total):
-        if step == W:
-            ev["t0"] = torch.cuda.Event(enable_timing=True)
-            ev["t0"].record()
-            marks["l0"] = ops.launch_count
-        if step == total:
-            ev["t1"] = torch.cuda.Event(enable_timing=True)
-            ev["t1"].record()
-
-    dist.barrier()
-    torch.cuda.synchronize()
-    if W == 0:
-        cb(0, W + K)
-    sch.denoise(model, cf, lat, ctx, device=dev, mask=mask, framestep=framestep, step_callback=cb, shard=shard)
-    dist.barrier()
-    torch.cuda.synchronize()
-    ms = torch.tensor([ev["t0"].elapsed_time(ev["t1"])], device=dev, dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    if rank == 0:
-        from bench import F_STEP, METRIC, UNIT, WORKLOAD  # type: ignore
-
-        line = {
-            "metric": METRIC, "value": K / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"temporal-shard x{world} (frames/rank {T // world}), "
-                       "K/V all-gather per layer over NCCL", "l2": "inputs larger than L2"},
-            "step_flops": F_STEP, "gpu_launches": ops.launch_count - marks["l0"],
-        }
-        print(json.dumps(line), flush=True)
-    dist.destroy_process_group()

@@ -52,14 +52,14 @@ def rms_norm(x, w, eps=1e-6):
 def timestep_embedding(t: torch.Tensor, channels: int) -> torch.Tensor:
     """diffusers Timesteps(num_channels, flip_sin_to_cos=False, downscale_freq_shift=0) (temporal_denoiser.py:57-61)."""
     half = channels // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     ang = t[:, None].float() * freqs[None]
     return torch.cat([ang.sin(), ang.cos()], dim=-1)
 
 
 def rotary_tables(head_dim: int, positions: torch.Tensor):
     """actionmesh/model/utils/rotary_embedding.py:10-69: theta_j = 10000^(-2j/d); cos/sin repeated per pair."""
-    inv = 1.0 / (10000.0 ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    inv = 1.0 / (10000.0 ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=positions.device) / head_dim))
     ph = torch.outer(positions.float(), inv)
     return ph.cos().repeat_interleave(2, dim=1), ph.sin().repeat_interleave(2, dim=1)
 
@@ -78,6 +78,30 @@ def frame_positions(framestep: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------------------------- attention
+def _sdpa_torch(q, k, v):
+    return F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)
+
+
+def sdpa_exact_chunked(q, k, v, rows: int = 4096):
+    """The same softmax(q k^T / sqrt(d)) v evaluated with explicit fp32 matmuls in query chunks, one head at a time: used
+    when the oracle runs on a CUDA device, where torch's fused SDPA kernels for fp32 inputs may route through TF32 tensor
+    cores (tests/test_default_config_gpu.py sets SDPA = sdpa_exact_chunked and disables TF32 matmuls)."""
+    B, H, Sq, D = q.shape
+    out = torch.empty(B, H, Sq, v.shape[-1], dtype=torch.float32, device=q.device)
+    scale = 1.0 / math.sqrt(D)
+    for b in range(B):
+        for h in range(H):
+            kt = k[b, h].float().t().contiguous()
+            vf = v[b, h].float()
+            for r0 in range(0, Sq, rows):
+                s = (q[b, h, r0:r0 + rows].float() @ kt) * scale
+                out[b, h, r0:r0 + rows] = torch.softmax(s, dim=-1) @ vf
+    return out
+
+
+SDPA = _sdpa_torch  # hook: the attention kernel the oracle calls (exact fp32 on a CPU torch)
+
+
 def attention(sd: dict, prefix: str, x: torch.Tensor, heads: int, *, context: Optional[torch.Tensor] = None,
               inflate_frames: Optional[int] = None, rope=None) -> torch.Tensor:
     """actionmesh/model/utils/attention_processor.py:36-168 (AttentionProcessor.__call__).
@@ -111,7 +135,7 @@ def attention(sd: dict, prefix: str, x: torch.Tensor, heads: int, *, context: Op
     if rope is not None:
         q = apply_rotary(q, *rope)
         k = apply_rotary(k, *rope)
-    o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)  # :133-139, scale 1/sqrt(dh)
+    o = SDPA(q, k, v)  # :133-139 F.scaled_dot_product_attention(dropout_p=0, is_causal=False), scale 1/sqrt(dh)
     o = o.transpose(1, 2).reshape(b, -1, heads * dh)
     o = o @ sd[prefix + "to_out.0.weight"].t() + sd[prefix + "to_out.0.bias"]
     if inflate_frames is not None:
@@ -172,14 +196,16 @@ def denoiser_forward(sd: dict, cfg: DenoiserConfig, hidden_states: torch.Tensor,
 class OracleDenoiser:
     """Duck-type of ActionMeshDenoiser for SchedulerFlow (scheduler.py:151-158): `.forward(hidden_states=, context=, ...)`."""
 
-    def __init__(self, state_dict: dict, cfg: DenoiserConfig):
-        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    def __init__(self, state_dict: dict, cfg: DenoiserConfig, device="cpu"):
+        self.device = torch.device(device)
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
         self.cfg = cfg
-        self.device = torch.device("cpu")
 
     @torch.no_grad()
     def forward(self, hidden_states, context, framestep, diffusion_time, mask=None, freqs_rot=None):
-        return denoiser_forward(self.sd, self.cfg, hidden_states, context, framestep, diffusion_time, mask, freqs_rot)
+        d = self.device
+        return denoiser_forward(self.sd, self.cfg, hidden_states.to(d), context.to(d), framestep.to(d),
+                                diffusion_time.to(d), None if mask is None else mask.to(d), freqs_rot)
 
 
 # --------------------------------------------------------------------------------------------------------- scheduler
@@ -232,11 +258,12 @@ def flow_denoise(model, init_latent, context, mask, framestep, *, num_inference_
     """scheduler.py:172-295 (_flow_sample + denoise), default actionmesh.yaml scheduler/cf_guidance settings."""
     latents = init_latent.clone()
     timesteps, distances = flow_schedule(num_inference_steps, shift=shift)
+    distances = distances.to(latents.device)
     unobserved = (mask == 0) if mask is not None else None
     freqs_rot = None
     for i, t in enumerate(timesteps[:-1]):
         h_in, c_in, m_in, f_in = cfg_batch(latents, context, mask, framestep, guidance_at_inference)
-        dtime = torch.tensor([float(t)], dtype=latents.dtype).expand(h_in.shape[0])
+        dtime = torch.tensor([float(t)], dtype=latents.dtype, device=latents.device).expand(h_in.shape[0])
         pred, freqs_rot = model.forward(hidden_states=h_in, context=c_in, framestep=f_in, mask=m_in,
                                         diffusion_time=dtime, freqs_rot=freqs_rot)
         pred = cfg_aggregate(pred, guidance_scales, len(guidance_at_inference))

@@ -21,6 +21,7 @@ from oracle import reference_loader, synth  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 TINY = dict(num_layers=5, num_attention_heads=2, width=256, cross_attention_dim=128, in_channels=64, mlp_ratio=4.0)
+MULTI_SEEDS = [(1234, 5), (11, 21), (12, 22), (13, 23), (14, 24), (15, 25), (16, 26), (17, 27)]
 WIDE = dict(num_layers=3, num_attention_heads=16, width=2048, cross_attention_dim=1024, in_channels=64, mlp_ratio=4.0)
 
 
@@ -100,6 +101,19 @@ def main():
     torch.save({"config": TINY, "seed": 1234, "input_seed": 5, "denoise4_out_autocast_bf16": den_ac.float(),
                 "rel_err_vs_fp32": float((den_ac.float()[0, 1:] - den[0, 1:]).norm() / den[0, 1:].norm())},
                os.path.join(GOLD, "denoiser_tiny_autocast.pt"))
+
+    # ---- the same pair of trajectories (fp32 and the reference's bf16 autocast recipe) for 8 (weight seed, input seed)
+    # draws: tests/test_chamfer_gpu.py compares the B200 path's Chamfer with the reference-autocast Chamfer in the MEAN
+    multi = {"config": TINY, "pairs": []}
+    for ws, isd in MULTI_SEEDS:
+        mm = _model(ns, TINY, ws)
+        lat_m, ctx_m, fs_m, mask_m = synth.make_inputs(1, 3, 31, 64, 9, 128, seed=isd)
+        d32 = sch.denoise(mm, cfg_b, lat_m.clone(), ctx_m, device="cpu", mask=mask_m, framestep=fs_m)
+        with torch.autocast(device_type="cpu", dtype=torch.bfloat16):
+            dac = sch.denoise(mm, cfg_b, lat_m.clone(), ctx_m, device="cpu", mask=mask_m, framestep=fs_m)
+        multi["pairs"].append({"seed": ws, "input_seed": isd, "denoise4_out": d32[0, 1:].clone(),
+                               "denoise4_out_autocast_bf16": dac.float()[0, 1:].clone()})
+    torch.save(multi, os.path.join(GOLD, "denoiser_tiny_multiseed.pt"))
 
     # ---- full-width 3-layer model (covers the skip block at D=2048, 16 heads, F=8192, Dc=1024)
     mw = _model(ns, WIDE, 77)

@@ -16,9 +16,11 @@ def _bf16r(t: torch.Tensor) -> torch.Tensor:
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def make_state_dict(cfg, seed: int = 1234, residual_scale: float | None = None) -> dict:
-    """cfg: any object with in_channels, num_layers, num_attention_heads, width, mlp_ratio, cross_attention_dim."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+def make_state_dict(cfg, seed: int = 1234, residual_scale: float | None = None, device="cpu") -> dict:
+    """cfg: any object with in_channels, num_layers, num_attention_heads, width, mlp_ratio, cross_attention_dim.
+    `device="cuda"` draws from a CUDA generator (the 1.44 B-parameter default config is generated on the GPU in the
+    full-depth parity test; the values differ from the CPU stream but both sides of a test always share one dict)."""
+    g = torch.Generator(device=device).manual_seed(seed)
     D, C, Dc = cfg.width, cfg.in_channels, cfg.cross_attention_dim
     F_ = int(D * cfg.mlp_ratio)
     dh = D // cfg.num_attention_heads
@@ -26,10 +28,10 @@ def make_state_dict(cfg, seed: int = 1234, residual_scale: float | None = None) 
 
     def lin(out_f, in_f, scale=1.0):
         b = 1.0 / math.sqrt(in_f)
-        return _bf16r((torch.rand(out_f, in_f, generator=g) * 2 - 1) * b * scale)
+        return _bf16r((torch.rand(out_f, in_f, generator=g, device=device) * 2 - 1) * b * scale)
 
     def vec(n, lo, hi):
-        return _bf16r(torch.rand(n, generator=g) * (hi - lo) + lo)
+        return _bf16r(torch.rand(n, generator=g, device=device) * (hi - lo) + lo)
 
     sd = {}
     sd["time_proj.linear_1.weight"], sd["time_proj.linear_1.bias"] = lin(4 * D, D), vec(4 * D, -0.02, 0.02)

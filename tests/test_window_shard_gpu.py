@@ -1,8 +1,15 @@
-"""Frame-sharded window on real GPUs (-m gpu; needs >= 2 devices, e.g. `gpurun --gpus 2`): the sharded denoise over 2
-ranks with the K/V all-gather must equal the single-GPU denoise of the same window (same kernels, different chunking of
-the key loop => only accumulation-order noise: rel <= 5e-3), observed frames bit-identical."""
+"""Frame-sharded window (-m gpu): the sharded denoise over W ranks with the per-layer K/V all-gather must equal the
+single-GPU denoise of the same window (same kernels, different chunking of the key loop => only accumulation-order noise:
+rel <= 5e-3), observed frames bit-identical.
+
+* `test_sharded_program_emulated_on_one_gpu`: W = 2, 4, 8 ranks EMULATED on one GPU — one host thread per rank runs the
+  unmodified `B200SchedulerFlow.denoise(..., shard=...)` with a `LocalShard` whose gathers are device copies between the
+  ranks' buffers (threading barriers stand in for the collective's rendezvous).  Covers frame slicing, the staggered
+  per-branch programs, the `kv_chunks` attention path and the latent gather end to end on the driver's 1-GPU box.
+* `test_sharded_window_matches_single_gpu`: the real thing over NCCL (needs >= 2 devices, e.g. `gpurun --gpus 2`)."""
 import os
 import socket
+import threading
 
 import pytest
 import torch
@@ -52,6 +59,91 @@ def _worker(rank, world, port, q):
         q.put((rank, repr(e)[:500]))
     finally:
         dist.destroy_process_group()
+
+
+class _LocalWorld:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class LocalShard:
+    """Stand-in for window_shard.FrameShard with every rank living in one process on one GPU (test infrastructure)."""
+
+    def __init__(self, lw: _LocalWorld, rank: int):
+        self.lw, self.rank, self.world, self.slot, self.group = lw, rank, lw.world, rank, None
+
+    def frames(self, n_frames):
+        from actionmesh_b200.window_shard import frame_partition
+
+        return frame_partition(n_frames, self.world, self.rank)
+
+    def _exchange(self, local):
+        lw = self.lw
+        lw.slots[self.rank] = local
+        lw.barrier.wait()                      # every rank has launched the kernels producing its `local`
+        parts = list(lw.slots)
+        return parts
+
+    def all_gather_kv(self, out, local):
+        parts = self._exchange(local)
+        rows = local.shape[0]
+        for r, part in enumerate(parts):       # same stream as the producers: ordered after them
+            out[r * rows:(r + 1) * rows].copy_(part)
+        self.lw.barrier.wait()                 # nobody overwrites its `local` before every copy has been enqueued
+
+        class _Done:
+            def wait(self_inner):
+                return None
+
+        return _Done()
+
+    def gather_latents(self, local):
+        parts = self._exchange(local)
+        out = torch.cat(list(parts), dim=1).clone()
+        self.lw.barrier.wait()
+        return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_program_emulated_on_one_gpu(amb_lib, world):
+    from actionmesh_b200.denoiser import B200Denoiser, DenoiserConfig
+    from actionmesh_b200.guidance import ClassifierFreeGuidance
+    from actionmesh_b200.scheduler import B200SchedulerFlow
+    from oracle import synth
+
+    d = dict(num_layers=3, num_attention_heads=2, width=256, cross_attention_dim=128, in_channels=64, mlp_ratio=4.0)
+    cfg = DenoiserConfig(inflated_layers=(0, 2), **d)  # one non-inflated layer exercises the local path too
+    model = B200Denoiser(cfg).to("cuda")
+    model.load_state_dict(synth.make_state_dict(cfg, 3))
+    lat, ctx, fs, mask = synth.make_inputs(1, 8, 63, 64, 9, 128, seed=8)
+    sch = B200SchedulerFlow(num_inference_steps=3, shift=3.0, is_additive=True)
+    cf = ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
+    ref = sch.denoise(model, cf, lat.clone().cuda(), ctx.cuda(), mask=mask.cuda(), framestep=fs).cpu()
+    lw = _LocalWorld(world)
+    outs, errs = [None] * world, []
+
+    def run(rank):
+        try:
+            torch.cuda.set_device(0)
+            outs[rank] = sch.denoise(model, cf, lat.clone().cuda(), ctx.cuda(), mask=mask.cuda(), framestep=fs,
+                                     shard=LocalShard(lw, rank)).cpu()
+        except Exception as exc:  # noqa: BLE001
+            errs.append((rank, repr(exc)[:400]))
+            lw.barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errs, errs
+    for r in range(world):
+        err = float((outs[r] - ref).norm() / ref.norm())
+        assert err < 5e-3, (r, err)
+        assert torch.equal(outs[r][0, 0], lat[0, 0])   # the observed frame comes back bit-identical on every rank
+    assert all(torch.equal(outs[0], o) for o in outs[1:])  # every rank ends with the same full window
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")

@@ -1,5 +1,5 @@
-"""Dump the clock64 role timeline of attention CTA (0,0,0) (v4 kernel): where each role waits.  AMB_ATTN_VER=4."""
-import math, os, sys
+"""Dump the clock64 role timeline of attention CTA (0,0,0) of the CTA-pair kernel: where each role waits."""
+import math, os, statistics, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
@@ -16,22 +16,18 @@ torch.cuda.synchronize()
 _lib.load_library().amb_debug_set_attn_trace(None)
 t = tr.cpu().view(5, 16, 8)
 t0 = int(t[4, 0, 0])
-names = ["t0h0", "t0h1", "t1h0", "t1h1", "mma"]
-print("softmax events: 0 enter, 1 s_full passed, 2 pass1 done, 3 max exchanged, 4 exps done, 5 arrived")
-print("mma events: 0 p_a0, 1 p_b0, 2 QK0' issued, 3 p_a1, 4 p_b1, 5 QK1' issued")
-for j in range(6):
-    for r in range(5):
-        ev = [int(x) - t0 for x in t[r, j, :6]]
-        print(f"j={100 + j} {names[r]:5s} " + " ".join(f"{e:7d}" for e in ev))
+print("softmax (warps 0 and 4): 0 enter, 1 s_full passed, 2 S loaded, 3 exps done, 4 P stored + arrived")
+print("mma: 0 iteration start, 1 QK(j+2) issued, 2 v_full passed, 3 p_ready passed, 4 PV(j) issued")
+for j in range(5):
+    for r, nme in ((0, "sm_w0"), (1, "sm_w4"), (4, "mma")):
+        print(f"j={100 + j} {nme:6s} " + " ".join(f"{int(x) - t0:7d}" for x in t[r, j, :5]))
     print()
-# averages
-import statistics
-for r in range(4):
+for r, nme in ((0, "sm_w0"), (1, "sm_w4")):
     d = t[r, 1:15]
-    print(names[r], "wait_s", statistics.mean((d[:, 1] - d[:, 0]).tolist()), "pass1", statistics.mean((d[:, 2] - d[:, 1]).tolist()),
-          "xchg", statistics.mean((d[:, 3] - d[:, 2]).tolist()), "exps", statistics.mean((d[:, 4] - d[:, 3]).tolist()),
-          "arrive", statistics.mean((d[:, 5] - d[:, 4]).tolist()))
+    print(nme, "period", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "wait_s", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
+          "load", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "exps", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
+          "store+arrive", statistics.mean((d[:, 4] - d[:, 3]).tolist()))
 d = t[4, 1:15]
-print("mma period", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "pa0->pb0", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
-      "pb0->qk0", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "qk0->pa1", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
-      "pa1->pb1", statistics.mean((d[:, 4] - d[:, 3]).tolist()), "pb1->qk1", statistics.mean((d[:, 5] - d[:, 4]).tolist()))
+print("mma period", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "k_wait+qk_issue", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
+      "v_wait", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "p_wait", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
+      "pv_issue", statistics.mean((d[:, 4] - d[:, 3]).tolist()))

@@ -298,10 +298,37 @@ def group_attn_perf(res):
     res["torch_sdpa_s32784"] = {"ms": ms, "TFLOPs": 4.0 * 2 * 16 * 32784 * 32784 * 128 / ms / 1e9}
 
 
+def group_attn_more(res):
+    """Shapes of the frame-sharded window, ragged chunks, a growing row maximum (slow path after the first tile)."""
+    import torch
+    from actionmesh_b200 import ops
+    _attn_case(res, "am_single", 1, 1, 1, 1, 128)
+    _attn_case(res, "am_q129_k129", 1, 3, 129, 129, 128)
+    _attn_case(res, "am_3tiles_tail1", 2, 2, 700, 257, 128)
+    _attn_case(res, "am_12tiles", 1, 2, 384, 1536, 128)
+    _attn_case(res, "am_chunks8", 1, 2, 2 * 2049, 8 * 2 * 2049, 128, kv_chunks=8)
+    _attn_case(res, "am_window_t2", 2, 16, 2 * 2049, 2 * 2049, 128, fused=True)
+    _attn_case(res, "am_sharp16", 1, 2, 512, 2048, 128, mode="sharp")
+    g = torch.Generator().manual_seed(5)
+    B, S, H, D = 1, 128 * 9 + 17, 2, 128
+    q = torch.randn(B, S, H, D, generator=g)
+    k = torch.randn(B, S, H, D, generator=g) * 0.05
+    v = torch.randn(B, S, H, D, generator=g)
+    qdir = q.mean(dim=1, keepdim=True)
+    qdir = qdir / qdir.norm(dim=-1, keepdim=True)
+    ramp = (torch.arange(S, dtype=torch.float32) / 128.0).floor()[None, :, None, None]
+    k = k + ramp * 12.0 * qdir * (math.sqrt(D) / (q * qdir).sum(-1, keepdim=True).abs().mean())
+    q, k, v = (t.cuda().bfloat16() for t in (q, k, v))
+    o = torch.empty_like(q)
+    ops.flash_attn(q, k, v, o, 1 / math.sqrt(D))
+    res["am_late_rescale"] = _err(o, _attn_ref(q, k, v, 1 / math.sqrt(D)))
+
+
 GROUPS = {
-    "elementwise": group_elementwise, "gemm": group_gemm, "attn": group_attn,
+    "elementwise": group_elementwise, "gemm": group_gemm, "attn": group_attn, "attn_more": group_attn_more,
     "gemm_perf": group_gemm_perf, "attn_perf": group_attn_perf,
 }
+TAG = os.environ.get("AMB_PROBE_TAG", "")
 
 
 def run_group(name):
@@ -317,7 +344,7 @@ def run_group(name):
         res["_trace"] = traceback.format_exc()[-1500:]
     res["_sec"] = time.time() - t0
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, f"probe_{name}.json"), "w") as f:
+    with open(os.path.join(OUT, f"probe_{name}{TAG}.json"), "w") as f:
         json.dump(res, f, indent=1)
     return res
 
@@ -330,14 +357,17 @@ def main():
     names = args or list(GROUPS)
     for n in names:
         t0 = time.time()
+        stale = os.path.join(OUT, f"probe_{n}{TAG}.json")
+        if os.path.exists(stale):
+            os.remove(stale)
         try:
             pr = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", n], capture_output=True, text=True,
                                 timeout=420)
             tail = (pr.stdout + pr.stderr)[-1200:]
         except subprocess.TimeoutExpired:
             tail = "TIMEOUT"
-        path = os.path.join(OUT, f"probe_{n}.json")
-        print(f"==== {n} ({time.time() - t0:.0f}s)")
+        path = os.path.join(OUT, f"probe_{n}{TAG}.json")
+        print(f"==== {n}{TAG} ({time.time() - t0:.0f}s)")
         if os.path.exists(path):
             r = json.load(open(path))
             for k, v in r.items():

@@ -1,5 +1,5 @@
-"""smoke(): one tiny denoiser step on cuda:0 checked against the fp32 oracle (the only place the package touches
-oracle/, and only as the checker)."""
+"""smoke(): one tiny denoiser step on cuda:0 checked against the fp32 oracle (test infrastructure: lives outside the
+product package; __graft_entry__.smoke() calls it)."""
 from __future__ import annotations
 
 import os
@@ -12,12 +12,11 @@ def smoke_check(verbose: bool = True) -> float:
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     if root not in sys.path:
         sys.path.insert(0, root)
+    from actionmesh_b200.denoiser import B200Denoiser, DenoiserConfig
+    from actionmesh_b200.guidance import ClassifierFreeGuidance
+    from actionmesh_b200.scheduler import B200SchedulerFlow
     from oracle import denoiser_oracle as do
     from oracle import synth
-
-    from .denoiser import B200Denoiser, DenoiserConfig
-    from .guidance import ClassifierFreeGuidance
-    from .scheduler import B200SchedulerFlow
 
     if not torch.cuda.is_available():
         raise RuntimeError("smoke() needs cuda:0")
