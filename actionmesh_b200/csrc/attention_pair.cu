@@ -13,17 +13,20 @@
 // always has independent work queued while the softmax warps turn S_j into P_j: the QKᵀ -> softmax -> P·V chain of one
 // tile no longer gates the next tile (the limiter of the single-CTA kernel, where S and P of a tile share one buffer).
 //
-// Warps (320 threads per CTA):
-//   0-7  softmax.  Warp w reads TMEM lanes 32(w%4) + 16(w/4) .. +15 with the 16x256b shape: a query row lives in ONE
-//        QUAD (thread t: rows t/4 and t/4+8, key columns 8g + 2(t%4), +1), so a row maximum is two shuffles — no
-//        cross-warp exchange, no block barrier on the per-tile path.  P goes back with the 16x128b shape, whose
-//        fragment (column 4g + t%4) is exactly the bf16 pair the thread just produced.
+// Warps (576 threads per CTA):
+//   0-15 softmax.  Warp w owns TMEM lanes 32(w%4) + 16((w/4)%2) .. +15 (16 query rows) and key half w/8 of every tile
+//        (64 keys), read with the 16x256b shape: a query row of that half lives in ONE QUAD (thread t: rows t/4 and
+//        t/4+8, key columns 8g + 2(t%4), +1), so row reductions are two shuffles.  P goes back with the 16x128b shape, whose
+//        fragment (column 4g + t%4) is exactly the bf16 pair the thread just produced; each key half keeps its P inside its
+//        own S columns (first 32 of its 64), so a half never overwrites scores the other half still has to read.
 //        The reference maximum of a row is fixed after its first key tile; later tiles only check (on the row sums they
-//        compute anyway) whether a probability left the safe range, and only then take the slow path: wait for the
-//        outstanding P·V, rescale the row's O and partial sum, recompute the tile.  Exact after the final 1/rowsum.
-//        exp2 runs on the MUFU and, for a compile-time share of the pairs, as a Cody-Waite + minimax cubic on the FMA pipe.
-//   8    TMA producer (both CTAs; bytes of the pair are credited to the leader's `full` barriers)
-//   9    MMA issuer (leader CTA only) + TMEM owner
+//        compute anyway) whether a probability left the safe range.  The two warps sharing 16 rows agree on that with one
+//        64-thread named barrier per tile; only then do they take the slow path together: exchange half-row maxima, wait
+//        for the outstanding P·V, rescale their halves of the rows' O columns and their partial sums, recompute the tile.
+//        Exact after the final 1/rowsum.  exp2 runs on the MUFU and, for a compile-time share of the pairs, as a
+//        Cody-Waite + minimax cubic on the FMA pipe.
+//   16   TMA producer (both CTAs; bytes of the pair are credited to the leader's `full` barriers)
+//   17   MMA issuer (leader CTA only) + TMEM owner
 #include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -31,10 +34,10 @@
 
 namespace amb {
 
-constexpr int PA_THREADS = 320;
+constexpr int PA_THREADS = 576;
 constexpr int PA_BK = 128;   // keys per K/V tile
 constexpr int PA_NBUF = 3;   // S/P buffers in TMEM
-constexpr float PA_SUM_LIMIT = 8192.0f;  // a thread's partial tile sum (32 keys) above this sends the warp down the slow path
+constexpr float PA_SUM_LIMIT = 4096.0f;  // a thread's partial tile sum (16 keys) above this sends its row group down the slow path
 
 template <int KS, int VS>
 struct PairSmem {
@@ -43,7 +46,9 @@ struct PairSmem {
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = Q_BYTES;
   static constexpr int V_OFF = K_OFF + KS * KV_BYTES;
-  static constexpr int BAR_OFF = V_OFF + VS * KV_BYTES;
+  static constexpr int XCH_OFF = V_OFF + VS * KV_BYTES;      // float[2 key halves][128 rows]: half-row maxima / sums
+  static constexpr int FLAG_OFF = XCH_OFF + 2 * 128 * 4;      // int[8 row groups][2 tile parities]: slow-path requests
+  static constexpr int BAR_OFF = FLAG_OFF + 8 * 2 * 4;
   static constexpr int NUM_BARS = 1 + 2 * KS + 2 * VS + 3 * PA_NBUF;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
@@ -60,13 +65,15 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   using L = PairSmem<KS, VS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
+  volatile int* flags = reinterpret_cast<volatile int*>(smem + L::FLAG_OFF);
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // leader's copy is live
   uint64_t* k_full = q_full + 1;          // [KS] leader
   uint64_t* k_empty = k_full + KS;        // [KS] both (multicast commit)
   uint64_t* v_full = k_empty + KS;        // [VS] leader
   uint64_t* v_empty = v_full + VS;        // [VS] both
   uint64_t* s_full = v_empty + VS;        // [3]  both: S_j complete in this CTA's TMEM
-  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: 16 warp arrivals (8 per CTA): P_j written
+  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: 32 warp arrivals (16 per CTA): P_j written
   uint64_t* pv_done = p_ready + PA_NBUF;  // [3]  both: P_j·V_j (and everything before it) complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + PA_NBUF);
 
@@ -80,19 +87,20 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const int tiles_per_chunk = (p.sk_chunk + PA_BK - 1) / PA_BK;
   const int n_kv = p.kv_chunks * tiles_per_chunk;
 
-  if (warp == 8 && lane == 0) {
+  if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 9) {
+  if (warp == 17) {
     if (lane == 0) {
+      for (int i = 0; i < 16; ++i) flags[i] = 0;
       mbar_init(q_full, 1);
       for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
       for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
       for (int b = 0; b < PA_NBUF; ++b) {
         mbar_init(&s_full[b], 1);
-        mbar_init(&p_ready[b], 16);
+        mbar_init(&p_ready[b], 32);
         mbar_init(&pv_done[b], 1);
       }
       fence_mbar_init();
@@ -106,7 +114,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == 16) {
     // ===================== TMA producer (both CTAs: my half of every tile) =====================
     if (elect_one()) {
       if (leader) mbar_expect_tx(q_full, 2 * L::Q_BYTES);
@@ -138,7 +146,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (++vs == VS) { vs = 0; vph ^= 1; }
       if (++jj == tiles_per_chunk) { jj = 0; ++chunk; }
     }
-  } else if (warp == 9) {
+  } else if (warp == 17) {
     if (leader) {
       // ===================== MMA issuer (leader CTA; one elected lane inside a converged warp) =====================
       constexpr uint32_t idesc_qk = make_idesc_bf16(256, PA_BK, 0, 0);
@@ -167,8 +175,9 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const uint32_t pa = tmem_base + buf * 128;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // 128 keys in 16-key steps: 8 packed P columns, 16 V rows (2 KB) per step
-            mma_ts_pair(o_tmem, pa + kk * 8, vd + 128 * kk, idesc_pv, (!first || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < 8; ++kk)  // 128 keys in 16-key steps: 8 packed P columns (key half h = kk / 4 keeps its P in
+                                          // the first 32 of its own 64 S columns), 16 V rows (2 KB) per step
+            mma_ts_pair(o_tmem, pa + (kk >> 2) * 64 + (kk & 3) * 8, vd + 128 * kk, idesc_pv, (!first || kk != 0) ? 1u : 0u);
           tc_commit_pair(&v_empty[vstage]);
           tc_commit_pair(&pv_done[buf]);
         }
@@ -211,22 +220,27 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
   } else {
-    // ===================== softmax: warp = (lane quarter, 16-row half); a row lives in one quad =====================
+    // ===================== softmax: warp = (lane quarter, 16-row half, key half) =====================
     const int quarter = warp & 3;
-    const int lane_base = quarter * 32 + (warp >> 2) * 16;
+    const int kh = warp >> 3;                                    // my key half of every tile: keys [64 kh, 64 kh + 64)
+    const int lane_base = quarter * 32 + ((warp >> 2) & 1) * 16;
     const uint32_t lane_sel = static_cast<uint32_t>(lane_base) << 16;
     const int row_a = lane_base + (lane >> 2);  // my two rows of this CTA's 128-row tile: row_a and row_a + 8
     const int qd = lane & 3;                    // my key columns inside a group of 8: 2 qd, 2 qd + 1
+    const int rg = warp & 7;                    // row group: the two warps rg and rg + 8 share 16 rows
+    const uint32_t pair_bar = 1 + rg;           // their 64-thread named barrier
     const float c = p.scale_log2;
     const uint64_t c2 = pk2(c, c);
     const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * PA_BK;  // valid keys in the last tile of a chunk
-    const uint32_t o_addr = tmem_base + PA_NBUF * 128 + lane_sel;
-    // debug timeline (amb_debug_set_attn_trace): roles 0/1 = softmax warps 0/4 of CTA (0,0,0), 5 x 16 x 8 int64 slots
-    const bool tracer = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && quarter == 0;
-    const int trole = warp >> 2;
+    const uint32_t o_addr = tmem_base + PA_NBUF * 128 + kh * 64 + lane_sel;   // my 64 columns of my rows' O
+    float* x_mine = xch + kh * 128;
+    const float* x_other = xch + (kh ^ 1) * 128;
+    // debug timeline (amb_debug_set_attn_trace): roles 0/1 = softmax warps 0/8 of CTA (0,0,0), 5 x 16 x 8 int64 slots
+    const bool tracer = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && rg == 0;
+    const int trole = kh;
 
-    float m_a = -INFINITY, m_b = -INFINITY;  // reference maxima (raw score units) of my two rows
-    float l_a = 0.f, l_b = 0.f;              // partial row sums: my 32 keys of every tile
+    float m_a = -INFINITY, m_b = -INFINITY;  // reference maxima (raw score units) of my two rows (same in both warps of a group)
+    float l_a = 0.f, l_b = 0.f;              // partial row sums: my 16 keys of every tile
 
     auto softmax_step = [&](int j, int buf, uint32_t bph, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
@@ -235,21 +249,20 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       mbar_wait(&s_full[buf], bph);
       if (tr) p.trace[(trole * 16 + (j - 100)) * 8 + 1] = clock64();
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + buf * 128 + lane_sel;
-      float s[64];  // s[4g + {0,1}] = row_a, keys 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
+      const uint32_t s_addr = tmem_base + buf * 128 + kh * 64 + lane_sel;
+      float s[32];  // s[4g + {0,1}] = row_a, keys 64 kh + 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
       tmem_ld16_256b_x8f(s_addr, s);
-      tmem_ld16_256b_x8f(s_addr + 64, s + 32);
       tmem_wait_ld();
       if (tr) p.trace[(trole * 16 + (j - 100)) * 8 + 2] = clock64();
 
-      uint32_t pk[32];
+      uint32_t pk[16];
       float ts_a, ts_b;
-      auto exps = [&]() {  // P = 2^(c s - c m) for my 64 scores, packed bf16 in the 16x128b fragment order; tile sums
+      auto exps = [&]() {  // P = 2^(c s - c m) for my 32 scores, packed bf16 in the 16x128b fragment order; tile sums
         const float mb_a = m_a * c, mb_b = m_b * c;
         const uint64_t nmb_a = pk2(-mb_a, -mb_a), nmb_b = pk2(-mb_b, -mb_b);
         uint64_t sum_a = pk2(0.f, 0.f), sum_b = pk2(0.f, 0.f);
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
+        for (int g = 0; g < 8; ++g) {
           float xa0, xa1, xb0, xb1, ea0, ea1, eb0, eb1;
           upk2(fma2(pk2(s[4 * g], s[4 * g + 1]), c2, nmb_a), xa0, xa1);
           upk2(fma2(pk2(s[4 * g + 2], s[4 * g + 3]), c2, nmb_b), xb0, xb1);
@@ -266,7 +279,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             eb1 = ex2_approx(xb1);
           }
           if (MASKED) {
-            const int key = 8 * g + 2 * qd;
+            const int key = kh * 64 + 8 * g + 2 * qd;
             if (key >= last_valid) ea0 = eb0 = 0.f;
             if (key + 1 >= last_valid) ea1 = eb1 = 0.f;
           }
@@ -285,17 +298,22 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       bool slow = (j == 0);
       if (!slow) {
         exps();
-        // probabilities outside the safe range show up in the sums computed anyway (inf / NaN included)
-        slow = __any_sync(0xffffffffu, !(ts_a < PA_SUM_LIMIT) || !(ts_b < PA_SUM_LIMIT));
+        // probabilities outside the safe range show up in the sums computed anyway (inf / NaN included); both warps of the
+        // row group must take the same decision: request flag (double-buffered by tile parity) + 64-thread barrier
+        volatile int* flag = flags + rg * 2 + (j & 1);
+        if (__any_sync(0xffffffffu, !(ts_a < PA_SUM_LIMIT) || !(ts_b < PA_SUM_LIMIT)) && lane == 0) *flag = 1;
+        named_bar_sync(pair_bar, 64);
+        slow = (*flag != 0);
       }
       if (slow) {
-        // (re)anchor my rows' reference maxima on this tile: row max inside the quad, rescale O and the partial sums
+        // (re)anchor the rows' reference maxima on this tile: half-row max inside the quad, exchange with the other key
+        // half through shared memory, then rescale my half of the rows' O columns and my partial sums
         float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
-        for (int g = 0; g < 16; ++g) {
+        for (int g = 0; g < 8; ++g) {
           float a0 = s[4 * g], a1 = s[4 * g + 1], b0 = s[4 * g + 2], b1 = s[4 * g + 3];
           if (MASKED) {
-            const int key = 8 * g + 2 * qd;
+            const int key = kh * 64 + 8 * g + 2 * qd;
             if (key >= last_valid) a0 = b0 = -INFINITY;
             if (key + 1 >= last_valid) a1 = b1 = -INFINITY;
           }
@@ -306,38 +324,42 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
         mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
         mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
-        const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+        if (qd == 0) {
+          x_mine[row_a] = mx_a;
+          x_mine[row_a + 8] = mx_b;
+        }
+        named_bar_sync(pair_bar, 64);
+        const float mn_a = fmaxf(m_a, fmaxf(mx_a, x_other[row_a])), mn_b = fmaxf(m_b, fmaxf(mx_b, x_other[row_a + 8]));
         if (j > 0) {
           const float al_a = ex2_approx((m_a - mn_a) * c), al_b = ex2_approx((m_b - mn_b) * c);
-          // every P·V issued so far has my P_{j-1} as an input, so it is either complete or about to be: wait for it,
-          // then O belongs to the softmax warps until P_j is handed over (P·V_j cannot start without my arrival)
+          // every P·V issued so far has this row group's P_{j-1} as an input, so it is either complete or about to be: wait
+          // for it, then O belongs to the softmax warps until P_j is handed over (P·V_j cannot start without my arrival)
           const int pbuf = buf == 0 ? PA_NBUF - 1 : buf - 1;
           mbar_wait(&pv_done[pbuf], buf == 0 ? (bph ^ 1) : bph);
           tc_fence_after();
-#pragma unroll 1
-          for (int hlf = 0; hlf < 2; ++hlf) {
-            float o[32];
-            tmem_ld16_256b_x8f(o_addr + hlf * 64, o);
-            tmem_wait_ld();
+          float o[32];
+          tmem_ld16_256b_x8f(o_addr, o);
+          tmem_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              o[4 * g] *= al_a;
-              o[4 * g + 1] *= al_a;
-              o[4 * g + 2] *= al_b;
-              o[4 * g + 3] *= al_b;
-            }
-            tmem_st16_256b_x8f(o_addr + hlf * 64, o);
+          for (int g = 0; g < 8; ++g) {
+            o[4 * g] *= al_a;
+            o[4 * g + 1] *= al_a;
+            o[4 * g + 2] *= al_b;
+            o[4 * g + 3] *= al_b;
           }
+          tmem_st16_256b_x8f(o_addr, o);
           tmem_wait_st();
           l_a *= al_a;
           l_b *= al_b;
+          if (kh == 0 && lane == 0) flags[rg * 2 + (j & 1)] = 0;
         }
         m_a = mn_a;
         m_b = mn_b;
         exps();
+        named_bar_sync(pair_bar, 64);  // exchange buffer and request flag are reusable; both halves' O columns are rescaled
       }
       if (tr) p.trace[(trole * 16 + (j - 100)) * 8 + 3] = clock64();
-      tmem_st16_128b_x16(s_addr, pk);  // P_j over the first 64 columns of S_j (all of this warp's S reads are complete)
+      tmem_st16_128b_x8(s_addr, pk);  // my half of P_j over the first 32 of my own 64 S columns (my S reads are complete)
       l_a += ts_a;
       l_b += ts_b;
       tmem_wait_st();
@@ -361,7 +383,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (++buf == PA_NBUF) { buf = 0; bph ^= 1; }
     }
 
-    // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d)
+    // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d); my 64 columns of my rows
     {
       const int lbuf = buf == 0 ? PA_NBUF - 1 : buf - 1;       // buffer of the last tile
       mbar_wait(&pv_done[lbuf], buf == 0 ? (bph ^ 1) : bph);  // its parity
@@ -370,29 +392,30 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
       l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
       l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
-      const float inv_a = 1.0f / l_a, inv_b = 1.0f / l_b;
+      if (qd == 0) {
+        x_mine[row_a] = l_a;
+        x_mine[row_a + 8] = l_b;
+      }
+      named_bar_sync(pair_bar, 64);
+      const float inv_a = 1.0f / (l_a + x_other[row_a]), inv_b = 1.0f / (l_b + x_other[row_a + 8]);
       const int qr_a = q0 + row_a, qr_b = qr_a + 8;
-      __nv_bfloat16* obase = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + 2 * qd;
+      __nv_bfloat16* obase = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + kh * 64 + 2 * qd;
       __nv_bfloat16* orow_a = obase + (long long)qr_a * p.o_stride_s;
       __nv_bfloat16* orow_b = obase + (long long)qr_b * p.o_stride_s;
-#pragma unroll 1
-      for (int hlf = 0; hlf < 2; ++hlf) {
-        float o[32];
-        tmem_ld16_256b_x8f(o_addr + hlf * 64, o);
-        tmem_wait_ld();
+      float o[32];
+      tmem_ld16_256b_x8f(o_addr, o);
+      tmem_wait_ld();
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int col = hlf * 64 + 8 * g;
-          if (qr_a < p.sq) *reinterpret_cast<uint32_t*>(orow_a + col) = pack_bf16(o[4 * g] * inv_a, o[4 * g + 1] * inv_a);
-          if (qr_b < p.sq) *reinterpret_cast<uint32_t*>(orow_b + col) = pack_bf16(o[4 * g + 2] * inv_b, o[4 * g + 3] * inv_b);
-        }
+      for (int g = 0; g < 8; ++g) {
+        if (qr_a < p.sq) *reinterpret_cast<uint32_t*>(orow_a + 8 * g) = pack_bf16(o[4 * g] * inv_a, o[4 * g + 1] * inv_a);
+        if (qr_b < p.sq) *reinterpret_cast<uint32_t*>(orow_b + 8 * g) = pack_bf16(o[4 * g + 2] * inv_b, o[4 * g + 3] * inv_b);
       }
     }
   }
 
   tc_fence_before();
   cluster_sync_all();  // neither CTA frees TMEM / exits while its peer may still read its shared memory or TMEM
-  if (warp == 9) {
+  if (warp == 17) {
     tc_fence_after();
     tmem_dealloc_pair(tmem_base, 512);
   }

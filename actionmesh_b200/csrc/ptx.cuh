@@ -164,11 +164,15 @@ __device__ __forceinline__ void tma_load_5d_pair(void* dst, const void* tmap, ui
         "r"(c2), "r"(c3), "r"(c4), "l"(hint)
       : "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster.  Default semantics (the form
+// CUTLASS's ClusterBarrier::arrive uses): one SYNCS.ARRIVE.RED, no memory fence.  The data these arrivals hand over lives
+// in TMEM / is ordered by tcgen05.wait + tcgen05.fence::before_thread_sync, not by the generic-proxy memory model; the
+// explicit `.release.cluster` form costs MEMBAR.ALL.GPU + ERRBAR per arrival (measured: 11 % of all stall samples of the
+// pair attention kernel, profiles/r02_ncu_attn_pair_v6a_summary.txt).
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {  // one warp in EACH CTA of the pair
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),

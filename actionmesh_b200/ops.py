@@ -14,16 +14,17 @@ from . import _lib
 
 launch_count = 0
 
-# Optional per-kernel CUDA-event timing (bench.py's roofline leg): when `event_log` is a list, flash_attn / gemm calls
-# whose `tag` is in `event_tags` append (tag, start_event, end_event) recorded on the launching stream.
+# Optional per-kernel CUDA-event timing (bench.py's roofline legs): when `event_log` is a list, launches whose `tag` is
+# in `event_tags` append (tag, start_event, end_event, meta) recorded on the launching stream; meta = the launch's shape.
 event_log = None
 event_tags: set = set()
 
 
 class _Timed:
-    def __init__(self, tag):
+    def __init__(self, tag, meta=None):
         self.on = event_log is not None and tag in event_tags
         self.tag = tag
+        self.meta = meta
 
     def __enter__(self):
         if self.on:
@@ -34,7 +35,7 @@ class _Timed:
     def __exit__(self, *a):
         if self.on:
             self.e1.record()
-            event_log.append((self.tag, self.e0, self.e1))
+            event_log.append((self.tag, self.e0, self.e1, self.meta))
 
 
 def on_device(fn):
@@ -107,9 +108,10 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
         raise _lib.AmbError(f"layernorm: unsupported dtype {x.dtype} -> {out.dtype}")
     if not out.is_cuda:
         raise _lib.AmbError("layernorm: out must be a CUDA tensor")
-    rc = _lib.load_library().amb_layernorm(
-        x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
-        int(out.dtype == torch.float32), out.stride(0), rows, cols, float(eps), _stream())
+    with _Timed("layernorm", (rows, cols, x.element_size() + out.element_size())):
+        rc = _lib.load_library().amb_layernorm(
+            x.data_ptr(), int(x.dtype == torch.float32), x.stride(0), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(),
+            int(out.dtype == torch.float32), out.stride(0), rows, cols, float(eps), _stream())
     _lib.check(rc, "amb_layernorm")
     launch_count += 1
     return out
@@ -342,7 +344,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         g.norm_w0 = g.norm_w1 = g.rope_cos = g.rope_sin = None
         g.norm_eps = 0.0
         g.rope_rows_per_pos = 1
-    with _Timed(tag):
+    with _Timed(tag, (m, n, k)):
         rc = _lib.load_library().amb_gemm_bf16(C.byref(g), _stream())
     _lib.check(rc, "amb_gemm_bf16")
     launch_count += 1
@@ -380,7 +382,7 @@ def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Ten
     a.kv_chunks = kv_chunks
     a.batch, a.heads, a.sq, a.head_dim = B, H, Sq, D
     a.scale = float(scale)
-    with _Timed(tag):
+    with _Timed(tag, (B, H, Sq, a.sk, D)):
         rc = _lib.load_library().amb_flash_attn_fwd(C.byref(a), _stream())
     _lib.check(rc, "amb_flash_attn_fwd")
     launch_count += 1

@@ -139,9 +139,10 @@ def test_sharded_program_emulated_on_one_gpu(amb_lib, world):
     for t in threads:
         t.join(timeout=300)
     assert not errs, errs
+    errors = [float((outs[r] - ref).norm() / ref.norm()) for r in range(world)]
+    print("SHARD_EMULATION", world, errors)
     for r in range(world):
-        err = float((outs[r] - ref).norm() / ref.norm())
-        assert err < 5e-3, (r, err)
+        assert errors[r] < 5e-3, (r, errors)
         assert torch.equal(outs[r][0, 0], lat[0, 0])   # the observed frame comes back bit-identical on every rank
     assert all(torch.equal(outs[0], o) for o in outs[1:])  # every rank ends with the same full window
 

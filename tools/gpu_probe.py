@@ -307,6 +307,8 @@ def group_attn_more(res):
     _attn_case(res, "am_3tiles_tail1", 2, 2, 700, 257, 128)
     _attn_case(res, "am_12tiles", 1, 2, 384, 1536, 128)
     _attn_case(res, "am_chunks8", 1, 2, 2 * 2049, 8 * 2 * 2049, 128, kv_chunks=8)
+    _attn_case(res, "am_chunks8_64keys", 1, 2, 64, 8 * 64, 128, kv_chunks=8)       # every tile is a ragged tail tile
+    _attn_case(res, "am_chunks4_200keys", 2, 2, 300, 4 * 200, 128, kv_chunks=4)
     _attn_case(res, "am_window_t2", 2, 16, 2 * 2049, 2 * 2049, 128, fused=True)
     _attn_case(res, "am_sharp16", 1, 2, 512, 2048, 128, mode="sharp")
     g = torch.Generator().manual_seed(5)
