@@ -78,9 +78,45 @@ __device__ __forceinline__ void load8_residual(const void* R, int r_fp32, long l
   }
 }
 
+// raw residual words of 32 consecutive columns (8 x 16 bytes of fp32, or 4 x 16 bytes of bf16): issued one chunk ahead of
+// their use so that the global-load latency hides behind the TMEM read, the math and the stores of the previous chunk
+struct Res32 {
+  uint4 w[8];
+};
+__device__ __forceinline__ void load_res32(const GemmParams& p, long long drow, int col, Res32& r) {
+  if (p.res_fp32) {
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p.residual) + drow * p.ldr + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.w[i] = q[i];
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + drow * p.ldr + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.w[i] = q[i];
+  }
+}
+__device__ __forceinline__ void add_res32(const GemmParams& p, const Res32& r, float* v) {
+  if (p.res_fp32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[4 * i] += __uint_as_float(r.w[i].x);
+      v[4 * i + 1] += __uint_as_float(r.w[i].y);
+      v[4 * i + 2] += __uint_as_float(r.w[i].z);
+      v[4 * i + 3] += __uint_as_float(r.w[i].w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f0 = unpack_bf16(r.w[i].x), f1 = unpack_bf16(r.w[i].y), f2 = unpack_bf16(r.w[i].z), f3 = unpack_bf16(r.w[i].w);
+      v[8 * i] += f0.x; v[8 * i + 1] += f0.y; v[8 * i + 2] += f1.x; v[8 * i + 3] += f1.y;
+      v[8 * i + 4] += f2.x; v[8 * i + 5] += f2.y; v[8 * i + 6] += f3.x; v[8 * i + 7] += f3.y;
+    }
+  }
+}
+
 // bias -> activation -> column scale -> residual -> store, for `NV` (multiple of 8) consecutive columns starting at col
 template <int NV>
-__device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, long long drow, int col, bool valid) {
+__device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, long long drow, int col, bool valid,
+                                                 const Res32* res = nullptr) {
   if (p.bias) {
 #pragma unroll
     for (int j = 0; j < NV; j += 4) {
@@ -100,6 +136,12 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
     }
   }
   if (!valid) return;
+  if (res != nullptr && NV == 32) {  // residual words were loaded a chunk ahead
+    add_res32(p, *res, v);
+#pragma unroll
+    for (int j = 0; j < NV; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col + j, v + j);
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < NV; j += 8) {
     if (p.residual) {
@@ -116,12 +158,12 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
 // per-head RMSNorm (+RoPE) path, then 16-byte global stores.  Shared by the 1-CTA and the 2-CTA kernels.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t taddr, int n0, int row, long long drow,
-                                              bool valid) {
+                                              bool valid, int c_begin = 0, int c_end = BN) {
   if (n0 < (p.norm_cols > p.rope_cols ? p.norm_cols : p.rope_cols)) {
     // ---- per-head RMSNorm and/or RoPE: one head = 128 accumulator columns, all owned by this thread ----
     if constexpr (BN % 128 == 0) {
 #pragma unroll 1
-      for (int hc = 0; hc < BN; hc += 128) {
+      for (int hc = c_begin; hc < c_end; hc += 128) {
         const int col0 = n0 + hc;
         float v[128];
 #pragma unroll
@@ -169,13 +211,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
       }
     }
   } else {
-    // ---- plain epilogue in 32-column chunks ----
+    // ---- plain epilogue in 32-column chunks; the residual words of chunk c+1 are in flight while chunk c is processed ----
+    const bool pre = p.residual != nullptr && valid;
+    Res32 rcur, rnext;
+    if (pre) load_res32(p, drow, n0 + c_begin, rcur);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       float v[32];
       tmem_ld_x32f(taddr + c, v);
+      if (pre && c + 32 < c_end) load_res32(p, drow, n0 + c + 32, rnext);
       tmem_wait_ld();
-      finish_and_store<32>(p, v, drow, n0 + c, valid);
+      finish_and_store<32>(p, v, drow, n0 + c, valid, pre ? &rcur : nullptr);
+      rcur = rnext;
     }
   }
 }
@@ -348,8 +395,10 @@ struct Gemm2Smem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
+constexpr int GEMM2_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (lane quarter x column half)
+
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = Gemm2Smem<STAGES>;
@@ -359,7 +408,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;  // [2]
-  uint64_t* tmem_empty = tmem_full + 2;      // [2] (leader's copy is the live one: 256 arrivals)
+  uint64_t* tmem_empty = tmem_full + 2;      // [2] (leader's copy is the live one: 16 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -380,7 +429,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tmem_full[a], 1);
-        mbar_init(&tmem_empty[a], 256);
+        mbar_init(&tmem_empty[a], 16);  // one arrival per epilogue warp of both CTAs
       }
       fence_mbar_init();
     }
@@ -453,8 +502,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5 of both CTAs; each CTA owns its 128 accumulator rows) =====================
+    // ===================== epilogue (warps 2..9 of both CTAs; each CTA owns its 128 accumulator rows; a warp owns the 32
+    // rows of its TMEM lane quarter and one 128-column half of the tile) =====================
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int row_in_tile = quarter * 32 + lane;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
@@ -469,10 +520,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN;
-      epilogue_tile<BN>(p, taddr, n0, row, drow, valid);
+      epilogue_tile<BN>(p, taddr, n0, row, drow, valid, chalf * 128, chalf * 128 + 128);
       tc_fence_before();
-      if (leader) mbar_arrive(&tmem_empty[acc]);
-      else mbar_arrive_remote(&tmem_empty[acc], 0);
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
     }
   }
 
@@ -521,7 +575,7 @@ static int launch_gemm2(const amb_gemm_args* a, cudaStream_t stream) {
   const int num_tiles = (a->n / 256) * ((a->m + 2 * BM - 1) / (2 * BM));
   int clusters = num_sms() / 2;
   if (clusters > num_tiles) clusters = num_tiles;
-  kern<<<2 * clusters, 192, L::TOTAL, stream>>>(tmA, tmA2, tmB, p);  // cluster dims are compiled in (__cluster_dims__)
+  kern<<<2 * clusters, GEMM2_THREADS, L::TOTAL, stream>>>(tmA, tmA2, tmB, p);  // cluster dims are compiled in (__cluster_dims__)
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -177,7 +177,7 @@ class B200Denoiser:
         sharded = shard is not None and shard.world > 1
         if sharded:
             assert nb == 1
-            kv_local, kv_all = ws["kv_local"][rows], ws["kv_all"][b0]          # kv_all[b]: (world, TL, 2D)
+            kv_all = ws["kv_all"][b0]                                           # kv_all[b]: (world, TL, 2D)
         S = st.ctx_kv[0].shape[0] // (B * T)
         sp = 0
         half = c.num_layers // 2
@@ -196,10 +196,12 @@ class B200Denoiser:
             ops.layernorm(h_in, w[p + "norm_s_attn.g"], w[p + "norm_s_attn.b"], 1e-5, out=xn)
             inflated = i in c.inflated_layers
             if sharded and inflated:
+                # this exchange's send buffer (a shard exchanging over peer memory double-buffers it, window_shard.py)
+                kv_local = shard.kv_local_view(ws["kv_local"], rows, b0) if hasattr(shard, "kv_local_view") else ws["kv_local"][rows]
                 ops.gemm(xn, w[p + "s.qkv"][D:], kv_local,
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nk"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
                                    rows_per_pos=L))
-                work = shard.all_gather_kv(kv_all.view(-1, 2 * D), kv_local)
+                work = shard.all_gather_kv(kv_all.view(-1, 2 * D), kv_local, b0)
                 ops.gemm(xn, w[p + "s.qkv"][:D], qkv[:, 0:D],
                          norm=dict(cols=D, seg=D, w0=w[p + "s.nq"], eps=1e-6, rope_cols=D, cos=rope_cos, sin=rope_sin,
                                    rows_per_pos=L))
@@ -338,7 +340,7 @@ class B200Denoiser:
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ workspaces
-    def _workspace(self, B: int, T: int, N: int, world: int = 1, slot: int = 0) -> dict:
+    def _workspace(self, B: int, T: int, N: int, world: int = 1, slot: int = 0, shard=None) -> dict:
         """Activation buffers of one window shape.  `slot` > 0 gives additional independent sets of the same shape (the
         single-GPU emulation of several ranks in tests/test_window_shard_gpu.py); one shape stays resident."""
         key = (B, T, N, world, slot)
@@ -366,7 +368,10 @@ class B200Denoiser:
             "pred": torch.empty(M, c.in_channels, dtype=bf, device=dev),
         }
         if world > 1:  # frame-sharded window: local [K|V] rows and the all-gathered buffer (one chunk per rank)
-            ws["kv_local"] = torch.empty(M, 2 * c.width, dtype=bf, device=dev)
+            if shard is not None and hasattr(shard, "empty_kv_local"):
+                ws["kv_local"] = shard.empty_kv_local(M, 2 * c.width, dev)     # symmetric memory mapped into every peer
+            else:
+                ws["kv_local"] = torch.empty(M, 2 * c.width, dtype=bf, device=dev)
             ws["kv_all"] = torch.empty(B, world, T * L, 2 * c.width, dtype=bf, device=dev)
         self._ws = {k: v for k, v in self._ws.items() if k[:4] == key[:4]}  # keep one shape resident
         self._ws[key] = ws

@@ -53,12 +53,20 @@ class B200ImageEncoder:
         self._pending_sd = None
         self.image_preprocess_dino = None
         self._gpu_preprocess = None
-        if pretrained_dino_feature_extractor is not None and os.path.isdir(pretrained_dino_feature_extractor):
+        # A given path must be a local checkpoint directory (the reference downloads 'facebook/dinov2-large' into
+        # pretrained_weights/dinov2 first, pipeline.py:75-78; there is no network here): a hub id or a missing directory is an
+        # error NOW, not a silent fall-back to default preprocessing and unloaded weights.
+        for what, path in (("pretrained_dino_feature_extractor", pretrained_dino_feature_extractor),
+                           ("pretrained_dino_model", pretrained_dino_model)):
+            if path is not None and not os.path.isdir(path):
+                raise AmbError(f"B200ImageEncoder: {what}={path!r} is not a local directory (download the checkpoint "
+                               "first, or pass None and call load_state_dict / init_random_)")
+        if pretrained_dino_feature_extractor is not None:
             from transformers import BitImageProcessor
             self.image_preprocess_dino = BitImageProcessor.from_pretrained(pretrained_dino_feature_extractor)
         if self.image_preprocess_dino is None:
             self.image_preprocess_dino = default_preprocessor()
-        if pretrained_dino_model is not None and os.path.isdir(pretrained_dino_model):
+        if pretrained_dino_model is not None:
             from safetensors.torch import load_file
             st = os.path.join(pretrained_dino_model, "model.safetensors")
             self._pending_sd = load_file(st) if os.path.exists(st) else torch.load(

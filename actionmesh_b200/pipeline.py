@@ -1,4 +1,4 @@
-"""Stage1Pipeline / AnimationPipeline — the hot path of `ActionMeshPipeline.__call__` (reference actionmesh/pipeline.py:602-685) without the
+"""ActionMeshB200Pipeline / Stage1Pipeline / AnimationPipeline — the hot path of `ActionMeshPipeline.__call__` (reference actionmesh/pipeline.py:602-685) without the
 out-of-scope stages: DinoV2 context for all frames (`encode_all_frames`, :232-245), then the autoregressive Stage-I
 denoising over 16-frame windows (`generate_3d_latents` :435-508 -> `_denoise_latents` :247-314).
 
@@ -8,19 +8,53 @@ them out of scope); the anchor latent therefore comes in through a seeded `Laten
 (`generate_mesh_animation` :510-600 -> `_decode_displacement` :316-385) on the CUDA autoencoder: the anchor mesh comes in
 as vertex features (positions + unit normals, mesh_processor.py:85-101) and the result is a `VertexBank` (all output
 meshes share the anchor's faces, so only vertices are produced).
+
+`ActionMeshB200Pipeline` is seam 4: the reference's constructor and `__call__(input, seed, stage_0_steps,
+face_decimation, floaters_threshold, stage_1_steps, guidance_scales, anchor_idx) -> list of meshes` (pipeline.py:47-53,
+602-613) built from `actionmesh_b200*.yaml` through the same `_target_` plumbing, with the out-of-scope stages (TripoSG,
+background removal, CPU cropping, mesh post-processing) as injected components.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, List, Optional
 
 import torch
 
+from ._lib import AmbError
+from .config import DEFAULT_CONFIG_DIR, get_target, instantiate, load_config
 from .denoiser import B200Denoiser
 from .guidance import ClassifierFreeGuidance
 from .image_encoder import B200ImageEncoder
 from .scheduler import B200SchedulerFlow
 from .windows import (LatentBank, VertexBank, apply_scaling, chunk_from, get_scaling, interpolate_timesteps)
+
+
+MIN_FRAMES = 16  # actionmesh/io/video_input.py:24
+
+
+@dataclass
+class ActionMeshInput:
+    """Same fields and checks as the reference's `ActionMeshInput` (actionmesh/io/video_input.py:27-55): N >= 16 RGB(A) PIL
+    frames and their float32 CPU timesteps.  The pipeline accepts the reference's own dataclass as well (duck-typed)."""
+    frames: list
+    timesteps: torch.Tensor
+
+    def __post_init__(self) -> None:
+        assert len(self.frames) >= MIN_FRAMES, f"At least {MIN_FRAMES} frames are required, got {len(self.frames)}"
+        assert self.timesteps.ndim == 1, f"Expected 1D timesteps, got {self.timesteps.ndim}D"
+        assert len(self.frames) == self.timesteps.shape[0], \
+            f"Number of frames ({len(self.frames)}) must match timesteps ({self.timesteps.shape[0]})"
+        assert self.timesteps.dtype == torch.float32, f"Expected float32 timesteps, got {self.timesteps.dtype}"
+        assert self.timesteps.device.type == "cpu", f"Expected CPU timesteps, got {self.timesteps.device}"
+
+    @property
+    def n_frames(self) -> int:
+        return len(self.frames)
+
+    def get(self, indices: torch.Tensor) -> "VideoInput":
+        return VideoInput([self.frames[int(i)] for i in indices], self.timesteps[indices])
 
 
 @dataclass
@@ -171,3 +205,200 @@ class AnimationPipeline(Stage1Pipeline):
         vb.update(timesteps=input.timesteps[self.anchor_idx:self.anchor_idx + 1],
                   vertices=[anchor_vertices.to(self.device, torch.float32)])
         return bank, self.generate_mesh_animation(bank, vb, anchor_normals)
+
+
+# ---------------------------------------------------------------------------------------------------- seam 4: the pipeline
+class PassThroughMeshProcess:
+    """Stand-in for the reference's CPU `MeshPostprocessor` (actionmesh/preprocessing/mesh_processor.py:374, decimation +
+    floater removal — out of scope): same constructor arguments / mutable attributes, `process_mesh` returns its input."""
+
+    def __init__(self, face_decimation: int = 40000, floaters_threshold: float = 0.02):
+        self.face_decimation = face_decimation
+        self.floaters_threshold = floaters_threshold
+
+    def process_mesh(self, mesh, seed: int = 44):
+        return mesh
+
+
+@dataclass
+class Mesh:
+    """Minimal mesh record returned when `trimesh` is not installed: (V, 3) float32 vertices + (F, 3) int faces (numpy)."""
+    vertices: "object"
+    faces: "object"
+
+
+def _vertex_normals(vertices: torch.Tensor, faces: torch.Tensor) -> torch.Tensor:
+    """Unit vertex normals of a triangle mesh (area-weighted face normals).  Used for the deformed anchor of clips spanning
+    several AR windows when trimesh is unavailable (the reference reads trimesh's `vertex_normals`, mesh_processor.py:98)."""
+    v0, v1, v2 = (vertices[faces[:, i]] for i in range(3))
+    fn = torch.cross(v1 - v0, v2 - v0, dim=-1)
+    vn = torch.zeros_like(vertices)
+    for i in range(3):
+        vn.index_add_(0, faces[:, i], fn)
+    return vn / vn.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+class ActionMeshB200Pipeline:
+    """Drop-in for `ActionMeshPipeline` on the B200 path: same constructor arguments, `.to(device)`, and `__call__`
+    signature / return value (reference actionmesh/pipeline.py:47-53,205,602-685).
+
+    Built from `actionmesh_b200.yaml` / `actionmesh_b200_fast.yaml` (the reference's YAML with the `_target_`s re-pointed):
+    scheduler, guidance, mesh post-process are instantiated at construction like the reference (:98-110); denoiser, image
+    encoder and autoencoder are resolved from their `_target_`s and loaded from `weights_dir` by `.to()` (or assigned
+    directly — `pipe.temporal_3D_denoiser = model` — when weights do not come from disk).  Injected, because out of scope:
+      image_to_3d(image=, generator=, num_inference_steps=, guidance_scale=) -> (anchor_latent, anchor_mesh)   [TripoSG]
+      background_removal.process_images(frames), image_process.process_images(frames)                          [CPU, optional]
+    `anchor_mesh` needs `.vertices`, `.faces` and `.vertex_normals` (the trimesh attributes the reference reads)."""
+
+    def __init__(self, config_name: str = "actionmesh_b200.yaml", config_dir: Optional[str] = None,
+                 dtype: torch.dtype = torch.bfloat16, lazy_loading: bool = False, *, image_to_3d=None,
+                 background_removal=None, image_process=None, weights_dir: str = "pretrained_weights/ActionMesh",
+                 config_updates: Optional[dict] = None):
+        self.cfg = load_config(config_name, config_dir or DEFAULT_CONFIG_DIR, updates=config_updates)
+        self._actionmesh_weights_dir = weights_dir
+        self.image_to_3d_pipe = image_to_3d
+        self.background_removal = background_removal
+        self.image_process = image_process
+        self.temporal_3D_denoiser = None
+        self.image_encoder = None
+        self.temporal_3D_vae = None
+        self._denoiser_latent_shape = tuple(self.cfg.denoiser_latent_shape)
+        self.mesh_process = instantiate(self.cfg.model.mesh_process, _convert_="partial")()
+        self.scheduler = instantiate(self.cfg.model.scheduler, _convert_="partial")()
+        self.cf_guidance = instantiate(self.cfg.model.cf_guidance, _convert_="partial")()
+        self._target_device = torch.device("cpu")
+        self._dtype = dtype            # accepted for signature compatibility: the CUDA path owns its precision recipe
+        self._lazy_loading = lazy_loading
+
+    # ---- model lifecycle (pipeline.py:117-229)
+    def _load_image_encoder(self) -> None:
+        if self.image_encoder is None:
+            self.image_encoder = instantiate(self.cfg.model.image_encoder, _convert_="partial")()
+        self.image_encoder.to(self._target_device)
+
+    def _load_temporal_denoiser(self) -> None:
+        if self.temporal_3D_denoiser is None:
+            cls = get_target(self.cfg.model.temporal_3D_denoiser["_target_"])
+            self.temporal_3D_denoiser = cls.from_pretrained(os.path.join(self._actionmesh_weights_dir, "denoiser"),
+                                                            device=self._target_device)
+        self.temporal_3D_denoiser.to(self._target_device)
+
+    def _load_temporal_vae(self) -> None:
+        if self.temporal_3D_vae is None:
+            cls = get_target(self.cfg.model.temporal_3D_vae["_target_"])
+            self.temporal_3D_vae = cls.from_pretrained(os.path.join(self._actionmesh_weights_dir, "autoencoder"),
+                                                       device=self._target_device)
+        self.temporal_3D_vae.to(self._target_device)
+
+    def _unload_model(self, attr: str) -> None:
+        if self._lazy_loading and getattr(self, attr, None) is not None:
+            setattr(self, attr, None)
+            torch.cuda.empty_cache()
+
+    def to(self, device) -> "ActionMeshB200Pipeline":
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise AmbError("ActionMeshB200Pipeline runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self._target_device = device
+        if not self._lazy_loading:
+            self._load_image_encoder()
+            self._load_temporal_denoiser()
+            self._load_temporal_vae()
+        return self
+
+    @property
+    def device(self) -> torch.device:
+        return self._target_device
+
+    # ---- stages
+    def init_banks_from_anchor(self, input, seed: int = 44):
+        """Stage 0 through the injected image-to-3D component (pipeline.py:387-433) -> (LatentBank, anchor mesh)."""
+        if self.image_to_3d_pipe is None:
+            raise AmbError("Stage 0 (TripoSG image-to-3D) is not part of actionmesh_b200: pass image_to_3d=<callable> "
+                           "returning (anchor_latent, anchor_mesh)")
+        gen_dev = getattr(self.image_to_3d_pipe, "device", self._target_device)
+        anchor_latent, anchor_mesh = self.image_to_3d_pipe(
+            image=input.frames[self.cfg.anchor_idx], generator=torch.Generator(device=gen_dev).manual_seed(seed),
+            num_inference_steps=self.cfg.model.image_to_3D_denoiser.num_inference_steps,
+            guidance_scale=self.cfg.model.image_to_3D_denoiser.guidance_scale)
+        anchor_mesh = self.mesh_process.process_mesh(anchor_mesh, seed=seed)
+        bank = LatentBank(empty_dims=self._denoiser_latent_shape)
+        bank.update(timesteps=input.timesteps[[self.cfg.anchor_idx]],
+                    latents=torch.as_tensor(anchor_latent).to(device=self._target_device, dtype=torch.float32))
+        return bank, anchor_mesh
+
+    def _stage_pipeline(self) -> "AnimationPipeline":
+        faces_holder = {}
+
+        def normals_fn(verts: torch.Tensor) -> torch.Tensor:
+            faces = faces_holder["faces"]
+            try:
+                import trimesh  # the reference's source of vertex normals
+
+                return torch.as_tensor(trimesh.Trimesh(vertices=verts.cpu().numpy(), faces=faces.cpu().numpy(),
+                                                       process=False).vertex_normals.copy(), dtype=torch.float32)
+            except ImportError:
+                return _vertex_normals(verts.to(torch.float32), faces.to(verts.device))
+
+        pipe = AnimationPipeline(self.temporal_3D_denoiser, self.scheduler, self.cf_guidance, self.temporal_3D_vae,
+                                 self.image_encoder, sliding_window_autoencoder=self.cfg.sliding_window_autoencoder,
+                                 subsampling_level=self.cfg.subsampling_level, normals_fn=normals_fn,
+                                 temporal_context_size=self.cfg.model.temporal_3D_denoiser.temporal_context_size,
+                                 sliding_window_denoiser=self.cfg.sliding_window_denoiser, anchor_idx=self.cfg.anchor_idx,
+                                 latent_shape=self._denoiser_latent_shape)
+        pipe._faces_holder = faces_holder
+        return pipe
+
+    @torch.no_grad()
+    def __call__(self, input, seed: int = 44, stage_0_steps: Optional[int] = None, face_decimation: Optional[int] = None,
+                 floaters_threshold: Optional[float] = None, stage_1_steps: Optional[int] = None,
+                 guidance_scales: Optional[List[float]] = None, anchor_idx: Optional[int] = None) -> list:
+        """video -> 4D (pipeline.py:602-685): returns the animated meshes (fixed topology) ordered by timestep."""
+        if stage_0_steps is not None:
+            self.cfg.model.image_to_3D_denoiser.num_inference_steps = stage_0_steps
+        if stage_1_steps is not None:
+            self.scheduler.num_inference_steps = stage_1_steps
+        if guidance_scales is not None:
+            self.cf_guidance.guidance_scales = guidance_scales
+        if face_decimation is not None:
+            self.mesh_process.face_decimation = face_decimation
+        if floaters_threshold is not None:
+            self.mesh_process.floaters_threshold = floaters_threshold
+        if anchor_idx is not None:
+            self.cfg.anchor_idx = anchor_idx
+        if self.background_removal is not None:
+            input.frames = self.background_removal.process_images(input.frames)
+        if self.image_process is not None:
+            input.frames = self.image_process.process_images(input.frames)
+
+        latent_bank, anchor_mesh = self.init_banks_from_anchor(input, seed)          # Stage 0
+        self._load_image_encoder()
+        vin = VideoInput(list(input.frames), input.timesteps)
+        self._load_temporal_denoiser()
+        self._load_temporal_vae()
+        stages = self._stage_pipeline()
+        context = stages.encode_all_frames(vin)                                       # DinoV2 on all frames
+        self._unload_model("image_encoder")
+        latent_bank = stages.generate_3d_latents(vin, context, latent_bank, seed=seed)   # Stage I
+        self._unload_model("temporal_3D_denoiser")
+        dev = self._target_device
+        verts = torch.as_tensor(anchor_mesh.vertices, dtype=torch.float32).to(dev)
+        faces = torch.as_tensor(anchor_mesh.faces).to(torch.int64)
+        normals = torch.as_tensor(anchor_mesh.vertex_normals, dtype=torch.float32).to(dev)
+        stages._faces_holder["faces"] = faces
+        vb = VertexBank(faces=faces)
+        vb.update(timesteps=input.timesteps[[self.cfg.anchor_idx]], vertices=[verts])
+        vb = stages.generate_mesh_animation(latent_bank, vb, normals)               # Stage II
+        self._unload_model("temporal_3D_vae")
+        ordered, _ = vb.get_ordered()
+        out = []
+        f_np = faces.cpu().numpy()
+        try:
+            import trimesh
+
+            for v in ordered:
+                out.append(trimesh.Trimesh(vertices=v.cpu().numpy(), faces=f_np, process=False))
+        except ImportError:
+            for v in ordered:
+                out.append(Mesh(vertices=v.cpu().numpy(), faces=f_np))
+        return out

@@ -128,7 +128,8 @@ class B200SchedulerFlow:
             m32 = torch.cat([mk if ul else torch.zeros_like(mk) for _, ul in branches], dim=0).reshape(K * B * T).contiguous()
             upd = (mk.reshape(B * T) == 0).to(torch.uint8)
         ws = model._workspace(K * B, T, N, world=shard.world if fsl is not None else 1,
-                              slot=getattr(shard, "slot", 0) if fsl is not None else 0)
+                              slot=getattr(shard, "slot", 0) if fsl is not None else 0,
+                              shard=shard if fsl is not None else None)
         L = N + 1
         sign = 1.0 if self.is_additive else -1.0
         t_dev = timesteps.to(dev)

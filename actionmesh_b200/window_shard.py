@@ -55,8 +55,19 @@ def configure_nccl_env() -> None:
     os.environ.setdefault("NCCL_MIN_NCHANNELS", "32")
 
 
+class _EventWork:
+    """`.wait()` with the semantics of an async NCCL work handle: the CURRENT stream waits for the recorded event."""
+
+    def __init__(self, event):
+        self.event = event
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.event)
+
+
 class FrameShard:
-    """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed."""
+    """Rank-local view of a frame-sharded window, handed to B200Denoiser._forward_packed.  The per-layer K/V exchange is an
+    NCCL all-gather on a dedicated high-priority communicator; `PeerFrameShard` replaces it with copy-engine peer copies."""
 
     def __init__(self, group=None):
         if group is None and dist.get_backend() == "nccl":
@@ -72,9 +83,9 @@ class FrameShard:
     def frames(self, n_frames: int) -> slice:
         return frame_partition(n_frames, self.world, self.rank)
 
-    def all_gather_kv(self, out: torch.Tensor, local: torch.Tensor):
+    def all_gather_kv(self, out: torch.Tensor, local: torch.Tensor, channel: int = 0):
         """Asynchronous all-gather of this rank's (rows, 2D) [K|V] of one layer/branch into `out` (world*rows, 2D),
-        rank-major; returns a handle whose `.wait()` makes the current stream wait for it."""
+        rank-major; returns a handle whose `.wait()` makes the current stream wait for it.  `channel` = the CFG branch."""
         return dist.all_gather_into_tensor(out, local, group=self.group, async_op=True)
 
     def gather_latents(self, local: torch.Tensor) -> torch.Tensor:
@@ -82,3 +93,64 @@ class FrameShard:
         out = torch.empty((self.world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out.view(-1, *local.shape[2:]), local[0].contiguous(), group=self.group)
         return out.reshape(1, -1, *local.shape[2:])
+
+
+class PeerFrameShard(FrameShard):
+    """The per-layer K/V exchange over NVLink peer memory with the COPY ENGINES instead of an NCCL kernel.
+
+    Why: next to SM-filling compute (persistent GEMMs, multi-wave attention) the cost of the all-gather is not its latency
+    but its SMs — NCCL's 32-channel kernel runs concurrently with the other CFG branch's attention / MLP and inflates their
+    time (timeline: profiles/r01_shard_profile_8gpu.log).  DMA copies take no SM.
+
+    How: every rank's K/V projection writes into a symmetric-memory buffer (torch.distributed._symmetric_memory: one
+    allocation per rank, mapped into every peer; `empty_kv_local` hands it to the denoiser's workspace).  `all_gather_kv`
+    then, on a side stream: wait for the projection -> device-side barrier across ranks (every rank's projection of this
+    layer / branch is complete) -> `world` contiguous peer->local copies (cudaMemcpyAsync D2D, own chunk first, peers in a
+    rank-rotated order so each NVLink port sees one reader at a time) -> event the attention launch waits on.
+    The local buffer is double-buffered by use parity: a rank writes parity p again two exchanges of the same branch later,
+    after it passed the barrier of the exchange in between, which every peer enters only after its own copies of this one
+    (stream order on its side stream)."""
+
+    def __init__(self, group=None):
+        super().__init__(group)
+        self._bufs = {}
+        self._uses = {}
+        self.stream = None
+
+    def empty_kv_local(self, rows: int, cols: int, device) -> torch.Tensor:
+        """(2, rows, cols) bf16 symmetric buffer; index [parity] is what the K/V projection of an exchange writes."""
+        import torch.distributed._symmetric_memory as symm_mem
+
+        key = (rows, cols)
+        if key not in self._bufs:
+            group = self.group if self.group is not None else dist.group.WORLD
+            buf = symm_mem.empty((2, rows, cols), dtype=torch.bfloat16, device=device)
+            hdl = symm_mem.rendezvous(buf, group)
+            peers = [buf if r == self.rank else hdl.get_buffer(r, (2, rows, cols), torch.bfloat16) for r in range(self.world)]
+            self._bufs[key] = (buf, hdl, peers)
+            self.stream = torch.cuda.Stream(device=device, priority=-1)
+        return self._bufs[key][0]
+
+    def kv_local_view(self, buf: torch.Tensor, rows: slice, channel: int) -> torch.Tensor:
+        """The rows of `buf` the next exchange on `channel` (= CFG branch) will send (alternating parity)."""
+        return buf[self._uses.get(channel, 0) & 1, rows]
+
+    def all_gather_kv(self, out: torch.Tensor, local: torch.Tensor, channel: int = 0):
+        key = next(k for k, v in self._bufs.items() if v[0].data_ptr() <= local.data_ptr() < v[0].data_ptr() + v[0].numel() * 2)
+        buf, hdl, peers = self._bufs[key]
+        off = (local.data_ptr() - buf.data_ptr()) // 2
+        n = local.numel()
+        rows = local.shape[0]
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream())
+        self._uses[channel] = self._uses.get(channel, 0) + 1
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            hdl.barrier(channel=channel)
+            for k in range(self.world):
+                r = (self.rank + k) % self.world
+                src = peers[r].view(-1)[off:off + n].view(rows, -1)
+                out[r * rows:(r + 1) * rows].copy_(src, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return _EventWork(done)

@@ -217,12 +217,12 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     shard = None
     if world > 1:
-        from actionmesh_b200.window_shard import FrameShard, configure_nccl_env
+        from actionmesh_b200.window_shard import FrameShard, PeerFrameShard, configure_nccl_env
 
         configure_nccl_env()  # NCCL protocol / channel defaults for the sharded window's K/V all-gather (before init)
         dist.init_process_group("nccl", device_id=dev)
         if T_WIN % world == 0:
-            shard = FrameShard()
+            shard = PeerFrameShard() if args.exchange == "peer" else FrameShard()
     K, W = args.steps, max(args.warmup, 0)
     T, N, C, S, Dc = T_WIN, N_TOK, C_LAT, S_CTX, D_CTX
     temporal_main = world > 1 and args.mode == "temporal" and shard is not None
@@ -367,7 +367,8 @@ def run_b200(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(repeats=3, warmup=1)
-    par = (f"temporal-shard x{world} ({T // world} frames/rank), K/V all-gather per layer over NCCL/NVLink" if temporal_main
+    xch = "copy-engine peer copies out of symmetric memory" if args.exchange == "peer" else "NCCL all-gather"
+    par = (f"temporal-shard x{world} ({T // world} frames/rank), K/V exchanged per layer over NVLink ({xch})" if temporal_main
            else (f"dp{world} (one window per GPU, no collective)" if world > 1 else "single"))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -514,6 +515,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="temporal", choices=["temporal", "dp"])
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+                    help="per-layer K/V exchange of the sharded window: NCCL all-gather or copy-engine peer copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true")
     ap.add_argument("--no-eager", action="store_true")

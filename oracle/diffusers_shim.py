@@ -182,3 +182,88 @@ def install() -> None:
     ap.Attention = Attention
     nm.FP32LayerNorm, nm.RMSNorm = FP32LayerNorm, RMSNorm
     em.Timesteps, em.TimestepEmbedding = Timesteps, TimestepEmbedding
+    _install_triposg_extras(mod, d, dm, ap, nm, em)
+
+
+# ---- what third_party/TripoSG's DiT and scheduler import on top (triposg_transformer.py:60-90, scheduling_rectified_flow.py:11-13)
+class _Config(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as exc:
+            raise AttributeError(k) from exc
+
+
+def register_to_config(init):
+    """diffusers.configuration_utils.register_to_config: record the constructor arguments (with defaults) in `self.config`."""
+    import functools
+
+    sig = inspect.signature(init)
+
+    @functools.wraps(init)
+    def wrapper(self, *args, **kwargs):
+        bound = sig.bind(self, *args, **kwargs)
+        bound.apply_defaults()
+        cfg = {k: v for k, v in bound.arguments.items() if k != "self"}
+        object.__setattr__(self, "_internal_config", _Config(cfg))
+        init(self, *args, **kwargs)
+
+    return wrapper
+
+
+class ConfigMixin:
+    @property
+    def config(self):
+        return self._internal_config
+
+
+class ModelMixin(nn.Module):
+    pass
+
+
+class SchedulerMixin:
+    pass
+
+
+class PeftAdapterMixin:
+    pass
+
+
+class LayerNorm(nn.LayerNorm):
+    """diffusers.models.normalization.LayerNorm(dim, eps=1e-5, elementwise_affine=True, bias=True) on torch >= 2.1."""
+
+    def __init__(self, dim, eps: float = 1e-5, elementwise_affine: bool = True, bias: bool = True):
+        super().__init__(dim, eps=eps, elementwise_affine=elementwise_affine, bias=bias)
+
+
+def _install_triposg_extras(mod, d, dm, ap, nm, em):
+    import dataclasses
+    import logging as pylog
+
+    cu = mod("diffusers.configuration_utils")
+    cu.ConfigMixin, cu.register_to_config = ConfigMixin, register_to_config
+    ld = mod("diffusers.loaders")
+    ld.PeftAdapterMixin = PeftAdapterMixin
+    mu = mod("diffusers.models.modeling_utils")
+    mu.ModelMixin = ModelMixin
+    ap.AttentionProcessor = object
+    nm.LayerNorm = LayerNorm
+    nm.AdaLayerNormContinuous = type("AdaLayerNormContinuous", (nn.Module,), {})
+    em.GaussianFourierProjection = type("GaussianFourierProjection", (nn.Module,), {})
+    em.apply_rotary_emb = lambda *a, **k: (_ for _ in ()).throw(NotImplementedError("apply_rotary_emb is not on the path"))
+    ut = mod("diffusers.utils")
+    ut.USE_PEFT_BACKEND = False
+    ut.is_torch_version = lambda op, v: True
+    ut.scale_lora_layers = lambda *a, **k: None
+    ut.unscale_lora_layers = lambda *a, **k: None
+    ut.logging = types.SimpleNamespace(get_logger=pylog.getLogger)
+    ut.BaseOutput = type("BaseOutput", (), {})
+    tu = mod("diffusers.utils.torch_utils")
+    tu.maybe_allow_in_graph = lambda cls: cls
+    ut.torch_utils = tu
+    sc = mod("diffusers.schedulers")
+    su = mod("diffusers.schedulers.scheduling_utils")
+    su.SchedulerMixin = SchedulerMixin
+    sc.scheduling_utils = su
+    d.configuration_utils, d.loaders, d.utils, d.schedulers = cu, ld, ut, sc
+    dm.modeling_utils = mu

@@ -21,6 +21,13 @@ from oracle import reference_loader, synth  # noqa: E402
 GOLD = os.path.join(ROOT, "tests", "golden")
 
 TINY = dict(num_layers=5, num_attention_heads=2, width=256, cross_attention_dim=128, in_channels=64, mlp_ratio=4.0)
+
+
+class TINY_CFG:
+    """Attribute view of TINY for oracle/synth.py."""
+    in_channels, num_layers, num_attention_heads, width, mlp_ratio, cross_attention_dim = 64, 5, 2, 256, 4.0, 128
+
+
 MULTI_SEEDS = [(1234, 5), (11, 21), (12, 22), (13, 23), (14, 24), (15, 25), (16, 26), (17, 27)]
 WIDE = dict(num_layers=3, num_attention_heads=16, width=2048, cross_attention_dim=1024, in_channels=64, mlp_ratio=4.0)
 
@@ -146,6 +153,32 @@ def main():
                 "query": qv, "displacement": disp, "chamfer_a": pa, "chamfer_b": pb,
                 "chamfer_n300": ch.compute_chamfer_score(pa, pb, n=300), "chamfer_all": ch.compute_chamfer_score(pa, pb, n=0)},
                os.path.join(GOLD, "autoencoder_tiny.pt"))
+
+    # ---- Stage 0: the vendored TripoSG DiT + RectifiedFlowScheduler (third_party/TripoSG, imported unchanged), tiny width:
+    # one forward and a 4-step CFG-2.0 denoising loop as TripoSGPipeline.__call__ drives them (pipeline_triposg.py:243-294)
+    tns = reference_loader.load_triposg()
+    tri = tns.TripoSGDiTModel(num_attention_heads=2, width=256, in_channels=64, num_layers=5, cross_attention_dim=128).eval()
+    tsd = synth.make_state_dict(TINY_CFG(), 4242)
+    from oracle import triposg_oracle as tro
+
+    inv = tro.remap_state_dict({k: k for k in tri.state_dict()})  # ActionMesh key name -> TripoSG key name
+    tri.load_state_dict({inv[k]: v for k, v in tsd.items()}, strict=True)
+    gg = torch.Generator().manual_seed(31)
+    x0 = torch.randn(1, 31, 64, generator=gg)
+    emb = torch.randn(1, 9, 128, generator=gg)
+    tt = torch.tensor([750.0, 750.0])
+    fwd = tri(torch.cat([x0, x0]), tt, encoder_hidden_states=torch.cat([torch.zeros_like(emb), emb]), return_dict=False)[0]
+    sched = tns.RectifiedFlowScheduler(num_train_timesteps=1000, shift=3.0)
+    sched.set_timesteps(4)
+    lat = x0.clone()
+    for t in sched.timesteps:
+        pred = tri(torch.cat([lat, lat]), t.expand(2), encoder_hidden_states=torch.cat([torch.zeros_like(emb), emb]),
+                   return_dict=False)[0]
+        unc, img = pred.chunk(2)
+        lat = sched.step(unc + 2.0 * (img - unc), t, lat, return_dict=False)[0]
+    torch.save({"config": TINY, "seed": 4242, "x0": x0, "image_embeds": emb, "t": tt, "forward_out": fwd, "shift": 3.0,
+                "timesteps": sched.timesteps.clone(), "sigmas": sched.sigmas.clone(), "denoise4_cfg2_out": lat,
+                "state_dict_keys": sorted(tri.state_dict().keys())}, os.path.join(GOLD, "triposg_tiny.pt"))
 
     for f in sorted(os.listdir(GOLD)):
         print(f, os.path.getsize(os.path.join(GOLD, f)))

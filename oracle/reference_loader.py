@@ -54,3 +54,19 @@ def load():
         embeddings=ref_embeddings,
     )
     return ns
+
+
+def load_triposg():
+    """The vendored TripoSG Stage-0 denoiser and scheduler (third_party/TripoSG @ fc5c409), imported unchanged."""
+    if not available():
+        raise RuntimeError(f"reference checkout not found at {REFERENCE_ROOT}")
+    from . import diffusers_shim
+
+    diffusers_shim.install()
+    root = os.path.join(REFERENCE_ROOT, "third_party", "TripoSG")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from triposg.models.transformers.triposg_transformer import TripoSGDiTModel
+    from triposg.schedulers.scheduling_rectified_flow import RectifiedFlowScheduler
+
+    return types.SimpleNamespace(TripoSGDiTModel=TripoSGDiTModel, RectifiedFlowScheduler=RectifiedFlowScheduler)

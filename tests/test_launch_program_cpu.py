@@ -118,7 +118,7 @@ def test_sharded_branch_programs_interleave(monkeypatch):
         group = None
 
         @staticmethod
-        def all_gather_kv(out, inp):
+        def all_gather_kv(out, inp, channel=0):
             assert out.shape[0] == world * inp.shape[0] and out.shape[1] == inp.shape[1]
             order.append(("gather", out.data_ptr()))
             return _Work(out.data_ptr())

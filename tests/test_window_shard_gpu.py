@@ -39,7 +39,7 @@ def _worker(rank, world, port, q):
         from actionmesh_b200.denoiser import B200Denoiser, DenoiserConfig
         from actionmesh_b200.guidance import ClassifierFreeGuidance
         from actionmesh_b200.scheduler import B200SchedulerFlow
-        from actionmesh_b200.window_shard import FrameShard
+        from actionmesh_b200.window_shard import FrameShard, PeerFrameShard
         from oracle import synth
 
         d = dict(num_layers=3, num_attention_heads=2, width=256, cross_attention_dim=128, in_channels=64, mlp_ratio=4.0)
@@ -51,10 +51,14 @@ def _worker(rank, world, port, q):
         cf = ClassifierFreeGuidance(guidance_at_inference=[[0, 1], [1, 1]], guidance_scales=[7.5])
         dev = f"cuda:{rank}"
         ref = sch.denoise(model, cf, lat.clone().to(dev), ctx.to(dev), mask=mask.to(dev), framestep=fs)
-        out = sch.denoise(model, cf, lat.clone().to(dev), ctx.to(dev), mask=mask.to(dev), framestep=fs, shard=FrameShard())
-        err = float((out - ref).norm() / ref.norm())
-        ok = err < 5e-3 and torch.equal(out[0, 0].cpu(), lat[0, 0])
-        q.put((rank, "ok" if ok else f"err {err}"))
+        res = []
+        for kind in (FrameShard, PeerFrameShard):   # NCCL all-gather / copy-engine peer copies out of symmetric memory
+            out = sch.denoise(model, cf, lat.clone().to(dev), ctx.to(dev), mask=mask.to(dev), framestep=fs, shard=kind())
+            err = float((out - ref).norm() / ref.norm())
+            res.append(err < 5e-3 and torch.equal(out[0, 0].cpu(), lat[0, 0]))
+            if not res[-1]:
+                res[-1] = f"{kind.__name__} err {err}"
+        q.put((rank, "ok" if all(r is True for r in res) else str(res)))
     except Exception as e:  # noqa: BLE001
         q.put((rank, repr(e)[:500]))
     finally:
@@ -86,7 +90,7 @@ class LocalShard:
         parts = list(lw.slots)
         return parts
 
-    def all_gather_kv(self, out, local):
+    def all_gather_kv(self, out, local, channel=0):
         parts = self._exchange(local)
         rows = local.shape[0]
         for r, part in enumerate(parts):       # same stream as the producers: ordered after them
