@@ -15,6 +15,7 @@ struct AttnParams {
   int kv_chunks, sk_chunk;   // kv split into chunks along the outermost tensor-map coordinate
   float scale_log2;          // scale * log2(e)
   long long* trace;          // optional device buffer for the clock64 timeline of CTA (0,0,0) (debug; NULL = off)
+  int* dirty;                // pair kernel: one flag per (batch, head, 256-row unit) the fast pass asks the exact pass to redo
 };
 
 // Q map is 4-D (d, s, head, batch); K/V maps are 5-D (d, key, head, batch, chunk) with free strides: one chunk per rank
@@ -54,6 +55,7 @@ inline AttnParams make_attn_params(const amb_attn_args* a, long long* trace) {
   p.sk_chunk = p.kv_chunks > 1 ? a->sk_chunk : a->sk;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.trace = trace;
+  p.dirty = nullptr;
   return p;
 }
 

@@ -27,6 +27,20 @@
 //        Cody-Waite + minimax cubic on the FMA pipe.
 //   16   TMA producer (both CTAs; bytes of the pair are credited to the leader's `full` barriers)
 //   17   MMA issuer (leader CTA only) + TMEM owner
+//
+// Two softmax organisations share everything else (MODE template parameter):
+//   FAST  (the one that runs): the 16 softmax warps form two SETS that take alternate key tiles (set 0 even, set 1 odd), so
+//         while one set sits in the latency phases of its tile (S visible, TMEM load, P store + hand-over) the other set
+//         keeps the MUFU / FMA pipes busy: ncu of the single-set version showed all warps in the same phase at the same
+//         time (53 % of a warp's time in the exponentials, competing; 47 % in latencies, all idle together —
+//         profiles/r02_ncu_attn_pair_v6b_summary.txt).  A warp owns 16 rows and ALL 128 keys of its tiles, processed as
+//         two 64-key halves handed to the tensor pipe separately (P·V of keys 0-63 overlaps the exponentials of 64-127).
+//         Both sets accumulate into the one O and use the row reference maxima fixed by set 0 on tile 0; there is NO
+//         in-loop rescale: a row whose probabilities leave the safe range marks its (batch, head, 256-row) unit dirty ...
+//   EXACT ... and the exact kernel (the single-set organisation described above, with the in-loop slow path) is launched
+//         right behind the fast one: it returns at once for clean units and recomputes dirty ones.  Results are exact either
+//         way; with q/k RMS-normalised as in this model the fix-up essentially never has work.
+#include <mutex>
 #include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -46,10 +60,10 @@ struct PairSmem {
   static constexpr int Q_OFF = 0;
   static constexpr int K_OFF = Q_BYTES;
   static constexpr int V_OFF = K_OFF + KS * KV_BYTES;
-  static constexpr int XCH_OFF = V_OFF + VS * KV_BYTES;      // float[2 key halves][128 rows]: half-row maxima / sums
-  static constexpr int FLAG_OFF = XCH_OFF + 2 * 128 * 4;      // int[8 row groups][2 tile parities]: slow-path requests
+  static constexpr int XCH_OFF = V_OFF + VS * KV_BYTES;      // float[3][128 rows]: row maxima / partial sums exchanged between warps
+  static constexpr int FLAG_OFF = XCH_OFF + 3 * 128 * 4;      // int[8 row groups][2 tile parities]: slow-path requests
   static constexpr int BAR_OFF = FLAG_OFF + 8 * 2 * 4;
-  static constexpr int NUM_BARS = 1 + 2 * KS + 2 * VS + 3 * PA_NBUF;
+  static constexpr int NUM_BARS = 1 + 2 * KS + 2 * VS + 4 * PA_NBUF;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
@@ -58,11 +72,18 @@ __host__ __device__ constexpr bool pa_emulated(int emu, int g, int r) {
   return emu == 0 ? false : emu == 1 ? (r == 0 && (g & 1) == 0) : emu == 2 ? (((g + r) & 1) == 0) : !(r == 1 && (g & 1) == 1);
 }
 
-template <int KS, int VS, int EMU>
+enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact on dirty units only / two-set fast path
+
+template <int KS, int VS, int EMU, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PA_THREADS, 1)
 flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                        const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using L = PairSmem<KS, VS>;
+  constexpr bool FAST = (MODE == PA_FAST);
+  const int unit = (blockIdx.z * gridDim.y + blockIdx.y) * (gridDim.x >> 1) + (blockIdx.x >> 1);
+  if (MODE == PA_FIXUP) {
+    if (p.dirty[unit] == 0) return;  // both CTAs of the pair read the same flag: uniform exit before any barrier exists
+  }
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
@@ -73,8 +94,9 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   uint64_t* v_full = k_empty + KS;        // [VS] leader
   uint64_t* v_empty = v_full + VS;        // [VS] both
   uint64_t* s_full = v_empty + VS;        // [3]  both: S_j complete in this CTA's TMEM
-  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: 32 warp arrivals (16 per CTA): P_j written
-  uint64_t* pv_done = p_ready + PA_NBUF;  // [3]  both: P_j·V_j (and everything before it) complete
+  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: P_j written.  EXACT: 32 warp arrivals (16 per CTA).  FAST: keys 0-63
+  uint64_t* p_half1 = p_ready + PA_NBUF;  // [3]  of P_j (8 warps of the owning set per CTA = 16 arrivals); keys 64-127 here
+  uint64_t* pv_done = p_half1 + PA_NBUF;  // [3]  both: P_j·V_j (and everything before it) complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + PA_NBUF);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -100,7 +122,8 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
       for (int b = 0; b < PA_NBUF; ++b) {
         mbar_init(&s_full[b], 1);
-        mbar_init(&p_ready[b], 32);
+        mbar_init(&p_ready[b], FAST ? 16 : 32);
+        mbar_init(&p_half1[b], 16);
         mbar_init(&pv_done[b], 1);
       }
       fence_mbar_init();
@@ -170,16 +193,18 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int buf, int vstage, bool first) {
+      auto issue_pv = [&](int buf, int vstage, bool first, int k0, int k1, bool last) {
         const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::KV_BYTES, 16384);
         const uint32_t pa = tmem_base + buf * 128;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // 128 keys in 16-key steps: 8 packed P columns (key half h = kk / 4 keeps its P in
+          for (int kk = k0; kk < k1; ++kk)  // 128 keys in 16-key steps: 8 packed P columns (key half h = kk / 4 keeps its P in
                                           // the first 32 of its own 64 S columns), 16 V rows (2 KB) per step
             mma_ts_pair(o_tmem, pa + (kk >> 2) * 64 + (kk & 3) * 8, vd + 128 * kk, idesc_pv, (!first || kk != 0) ? 1u : 0u);
-          tc_commit_pair(&v_empty[vstage]);
-          tc_commit_pair(&pv_done[buf]);
+          if (last) {
+            tc_commit_pair(&v_empty[vstage]);
+            tc_commit_pair(&pv_done[buf]);
+          }
         }
         __syncwarp();
       };
@@ -212,7 +237,14 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         mbar_wait(&p_ready[buf], bph);
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 3] = clock64();
         tc_fence_after();
-        issue_pv(buf, vs, j == 0);
+        if (FAST) {  // P·V of keys 0-63 starts while the owning set still works on keys 64-127
+          issue_pv(buf, vs, j == 0, 0, 4, false);
+          mbar_wait(&p_half1[buf], bph);
+          tc_fence_after();
+          issue_pv(buf, vs, j == 0, 4, 8, true);
+        } else {
+          issue_pv(buf, vs, j == 0, 0, 8, true);
+        }
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 4] = clock64();
         if (++vs == VS) { vs = 0; vph ^= 1; }
         if (++buf == PA_NBUF) { buf = 0; bph ^= 1; }
@@ -220,6 +252,166 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
     }
   } else {
+    if constexpr (FAST) {
+    // ===================== softmax, FAST: warp = (set, lane quarter, 16-row half); set s takes tiles j = s, s+2, ... ============
+    const int set = warp >> 3;
+    const int quarter = warp & 3;
+    const int lane_base = quarter * 32 + ((warp >> 2) & 1) * 16;
+    const uint32_t lane_sel = static_cast<uint32_t>(lane_base) << 16;
+    const int row_a = lane_base + (lane >> 2);  // my two rows of this CTA's 128-row tile: row_a and row_a + 8
+    const int qd = lane & 3;                    // my key columns inside a group of 8: 2 qd, 2 qd + 1
+    const float c = p.scale_log2;
+    const uint64_t c2 = pk2(c, c);
+    const int last_valid = p.sk_chunk - (tiles_per_chunk - 1) * PA_BK;  // valid keys in the last tile of a chunk
+    const bool has_tail = last_valid < PA_BK;
+    constexpr uint32_t MREF_BAR = 1, SUM_BAR = 2;  // named barriers: reference maxima published / partial sums published
+    // debug timeline (amb_debug_set_attn_trace): roles 0/1 = warp 0 of each set of CTA (0,0,0), 5 x 16 x 8 int64 slots
+    const bool tracer = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (warp & 7) == 0;
+
+    float m_a = 0.f, m_b = 0.f;  // reference maxima (raw score units) of my two rows: fixed by set 0 on tile 0
+    float l_a = 0.f, l_b = 0.f;  // partial row sums: my 32 keys of every tile of my set
+    bool dirty = false;
+
+    auto half_step = [&](int j, int buf, int h, bool masked) {
+      const bool tr = tracer && j >= 100 && j < 116;
+      const uint32_t s_addr = tmem_base + buf * 128 + h * 64 + lane_sel;
+      float s[32];  // s[4g + {0,1}] = row_a, keys 64 h + 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
+      tmem_ld16_256b_x8f(s_addr, s);
+      tmem_wait_ld();
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 2 + 2 * h] = clock64();
+      uint32_t pk[16];
+      const float mb_a = m_a * c, mb_b = m_b * c;
+      const uint64_t nmb_a = pk2(-mb_a, -mb_a), nmb_b = pk2(-mb_b, -mb_b);
+      uint64_t sum_a = pk2(0.f, 0.f), sum_b = pk2(0.f, 0.f);
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        float xa0, xa1, xb0, xb1, ea0, ea1, eb0, eb1;
+        upk2(fma2(pk2(s[4 * g], s[4 * g + 1]), c2, nmb_a), xa0, xa1);
+        upk2(fma2(pk2(s[4 * g + 2], s[4 * g + 3]), c2, nmb_b), xb0, xb1);
+        if (pa_emulated(EMU, g, 0)) {
+          exp2_poly2(xa0, xa1, ea0, ea1);
+        } else {
+          ea0 = ex2_approx(xa0);
+          ea1 = ex2_approx(xa1);
+        }
+        if (pa_emulated(EMU, g, 1)) {
+          exp2_poly2(xb0, xb1, eb0, eb1);
+        } else {
+          eb0 = ex2_approx(xb0);
+          eb1 = ex2_approx(xb1);
+        }
+        if (masked) {
+          const int key = h * 64 + 8 * g + 2 * qd;
+          if (key >= last_valid) ea0 = eb0 = 0.f;
+          if (key + 1 >= last_valid) ea1 = eb1 = 0.f;
+        }
+        sum_a = add2(sum_a, pk2(ea0, ea1));
+        sum_b = add2(sum_b, pk2(eb0, eb1));
+        pk[2 * g] = pack_bf16(ea0, ea1);
+        pk[2 * g + 1] = pack_bf16(eb0, eb1);
+      }
+      float x0, x1, y0, y1;
+      upk2(sum_a, x0, x1);
+      upk2(sum_b, y0, y1);
+      const float ts_a = x0 + x1, ts_b = y0 + y1;
+      // probabilities outside the safe range show up in the sums computed anyway (inf / NaN included): the unit is redone
+      dirty |= !(ts_a < PA_SUM_LIMIT) || !(ts_b < PA_SUM_LIMIT);
+      tmem_st16_128b_x8(s_addr, pk);  // this half of P_j over the first 32 of its own 64 S columns
+      l_a += ts_a;
+      l_b += ts_b;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        uint64_t* bar = h ? &p_half1[buf] : &p_ready[buf];
+        if (leader) mbar_arrive(bar);
+        else mbar_arrive_remote(bar, 0);
+      }
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 3 + 2 * h] = clock64();
+    };
+
+    for (int j = set; j < n_kv; j += 2) {
+      const int buf = j % PA_NBUF;
+      const uint32_t bph = (j / PA_NBUF) & 1;
+      const bool masked = has_tail && (j % tiles_per_chunk == tiles_per_chunk - 1);
+      const bool tr = tracer && j >= 100 && j < 116;
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 0] = clock64();
+      mbar_wait(&s_full[buf], bph);
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 1] = clock64();
+      tc_fence_after();
+      if (j == 0) {
+        // set 0 anchors every row's reference maximum on tile 0 and publishes it to set 1
+        float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          float s[32];
+          tmem_ld16_256b_x8f(tmem_base + h * 64 + lane_sel, s);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float a0 = s[4 * g], a1 = s[4 * g + 1], b0 = s[4 * g + 2], b1 = s[4 * g + 3];
+            if (masked) {
+              const int key = h * 64 + 8 * g + 2 * qd;
+              if (key >= last_valid) a0 = b0 = -INFINITY;
+              if (key + 1 >= last_valid) a1 = b1 = -INFINITY;
+            }
+            mx_a = fmaxf(mx_a, fmaxf(a0, a1));
+            mx_b = fmaxf(mx_b, fmaxf(b0, b1));
+          }
+        }
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+        m_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+        m_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        if (n_kv > 1) {
+          if (qd == 0) {
+            xch[row_a] = m_a;
+            xch[row_a + 8] = m_b;
+          }
+          __syncwarp();
+          named_bar_arrive(MREF_BAR, 512);
+        }
+      } else if (j == 1) {
+        named_bar_sync(MREF_BAR, 512);
+        m_a = xch[row_a];
+        m_b = xch[row_a + 8];
+      }
+      half_step(j, buf, 0, masked);
+      half_step(j, buf, 1, masked);
+    }
+    if (__any_sync(0xffffffffu, dirty) && lane == 0) atomicOr(p.dirty + unit, 1);
+
+    // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d); set s normalises columns [64 s, 64 s + 64) of its rows
+    {
+      const int jl = n_kv - 1;
+      mbar_wait(&pv_done[jl % PA_NBUF], (jl / PA_NBUF) & 1);
+      tc_fence_after();
+      l_a += __shfl_xor_sync(0xffffffffu, l_a, 1);
+      l_b += __shfl_xor_sync(0xffffffffu, l_b, 1);
+      l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+      l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+      float* x_mine = xch + 128 + set * 128;  // (the first 128 floats hold the reference maxima)
+      const float* x_other = xch + 128 + (set ^ 1) * 128;
+      if (qd == 0) {
+        x_mine[row_a] = l_a;
+        x_mine[row_a + 8] = l_b;
+      }
+      named_bar_sync(SUM_BAR, 512);
+      const float inv_a = 1.0f / (l_a + x_other[row_a]), inv_b = 1.0f / (l_b + x_other[row_a + 8]);
+      const int qr_a = q0 + row_a, qr_b = qr_a + 8;
+      __nv_bfloat16* obase = p.o + (long long)batch * p.o_stride_b + (long long)head * p.o_stride_h + set * 64 + 2 * qd;
+      __nv_bfloat16* orow_a = obase + (long long)qr_a * p.o_stride_s;
+      __nv_bfloat16* orow_b = obase + (long long)qr_b * p.o_stride_s;
+      float o[32];
+      tmem_ld16_256b_x8f(tmem_base + PA_NBUF * 128 + set * 64 + lane_sel, o);
+      tmem_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (qr_a < p.sq) *reinterpret_cast<uint32_t*>(orow_a + 8 * g) = pack_bf16(o[4 * g] * inv_a, o[4 * g + 1] * inv_a);
+        if (qr_b < p.sq) *reinterpret_cast<uint32_t*>(orow_b + 8 * g) = pack_bf16(o[4 * g + 2] * inv_b, o[4 * g + 3] * inv_b);
+      }
+    }
+    } else {
     // ===================== softmax: warp = (lane quarter, 16-row half, key half) =====================
     const int quarter = warp & 3;
     const int kh = warp >> 3;                                    // my key half of every tile: keys [64 kh, 64 kh + 64)
@@ -411,6 +603,8 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         if (qr_b < p.sq) *reinterpret_cast<uint32_t*>(orow_b + 8 * g) = pack_bf16(o[4 * g + 2] * inv_b, o[4 * g + 3] * inv_b);
       }
     }
+    }
+    if (MODE == PA_FIXUP && warp == 0 && lane == 0 && leader) p.dirty[unit] = 0;  // (every thread of the pair has read it)
   }
 
   tc_fence_before();
@@ -421,22 +615,61 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   }
 }
 
+// Scratch of the fast pass -> exact pass hand-over: one int per unit, zero between launches (the exact pass clears what it
+// redoes).  One buffer per (device, stream): launches on different streams never share flags.
+constexpr int PA_MAX_UNITS = 1 << 18;
+static int* pair_dirty_flags(cudaStream_t stream) {
+  struct Slot { int dev; cudaStream_t stream; int* ptr; };
+  static Slot slots[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  for (auto& sl : slots) {
+    if (sl.ptr && sl.dev == dev && sl.stream == stream) return sl.ptr;
+    if (!sl.ptr) {
+      if (cudaMalloc(&sl.ptr, PA_MAX_UNITS * sizeof(int)) != cudaSuccess) { sl.ptr = nullptr; return nullptr; }
+      if (cudaMemsetAsync(sl.ptr, 0, PA_MAX_UNITS * sizeof(int), stream) != cudaSuccess) return nullptr;  // stream-ordered before its first use
+      sl.dev = dev;
+      sl.stream = stream;
+      return sl.ptr;
+    }
+  }
+  return nullptr;
+}
+
 int launch_attn_pair(const amb_attn_args* a, long long* trace, cudaStream_t stream) {
   constexpr int KS = 4, VS = 4;
   using L = PairSmem<KS, VS>;
   CUtensorMap tmQ, tmK, tmV;
   int r = encode_attn_maps(a, 128, 128, 64, 128, &tmQ, &tmK, &tmV);
   if (r) return r;
-  const AttnParams p = make_attn_params(a, trace);
+  AttnParams p = make_attn_params(a, trace);
   dim3 grid(2 * ((a->sq + 255) / 256), a->heads, a->batch);  // cluster dims (2,1,1) are compiled in
-  static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 2; }();  // development switch
-  auto kern = emu == 0 ? flash_attn_pair_kernel<KS, VS, 0>
-            : emu == 1 ? flash_attn_pair_kernel<KS, VS, 1>
-            : emu == 3 ? flash_attn_pair_kernel<KS, VS, 3>
-                       : flash_attn_pair_kernel<KS, VS, 2>;
-  r = ensure_smem_optin(kern, L::TOTAL);
+  const long long units = (long long)(grid.x / 2) * grid.y * grid.z;
+  static const int mode = []() { const char* e = getenv("AMB_ATTN_MODE"); return e ? atoi(e) : 2; }();  // development switch: 0 = exact only
+  static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 1; }();    // development switch
+  auto exact = flash_attn_pair_kernel<KS, VS, 1, PA_EXACT>;
+  if (mode == 0 || units > PA_MAX_UNITS) {
+    r = ensure_smem_optin(exact, L::TOTAL);
+    if (r) return r;
+    exact<<<grid, PA_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+    AMB_CHECK_CUDA(cudaGetLastError());
+    return AMB_OK;
+  }
+  p.dirty = pair_dirty_flags(stream);
+  AMB_CHECK_ARG(p.dirty != nullptr, "flash_attn: could not allocate the fix-up flags");
+  auto fast = emu == 0 ? flash_attn_pair_kernel<KS, VS, 0, PA_FAST>
+            : emu == 2 ? flash_attn_pair_kernel<KS, VS, 2, PA_FAST>
+                       : flash_attn_pair_kernel<KS, VS, 1, PA_FAST>;
+  auto fixup = flash_attn_pair_kernel<KS, VS, 1, PA_FIXUP>;
+  r = ensure_smem_optin(fast, L::TOTAL);
   if (r) return r;
-  kern<<<grid, PA_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  r = ensure_smem_optin(fixup, L::TOTAL);
+  if (r) return r;
+  fast<<<grid, PA_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  fixup<<<grid, PA_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);  // returns at once for every unit the fast pass left clean
   AMB_CHECK_CUDA(cudaGetLastError());
   return AMB_OK;
 }

@@ -165,31 +165,43 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
 #pragma unroll 1
       for (int hc = c_begin; hc < c_end; hc += 128) {
         const int col0 = n0 + hc;
-        float v[128];
+        // Two passes over the head's 128 accumulator columns, 32 at a time (TMEM re-reads are cheap, registers are not:
+        // 10 warps are budgeted as 12, i.e. 168 registers per thread): sum of squares first, then scale / rotate / store.
+        float rs = 1.0f;
+        const bool do_norm = col0 < p.norm_cols, do_rope = col0 < p.rope_cols;
+        if (do_norm) {
+          float ss = 0.f;
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld_x32f(taddr + hc + c * 32, v);
+            tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32f(taddr + hc + c * 32, v + c * 32);
-        tmem_wait_ld();
-        if (col0 < p.norm_cols || col0 < p.rope_cols) {
-          if (col0 < p.norm_cols) {
-            float ss = 0.f;
+            for (int j = 0; j < 32; ++j) ss += v[j] * v[j];
+          }
+          rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
+        }
+        const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
+        const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
+        const float* cs = p.rope_cos + (long long)pos * 64;
+        const float* sn = p.rope_sin + (long long)pos * 64;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float v[32];
+          tmem_ld_x32f(taddr + hc + c * 32, v);
+          tmem_wait_ld();
+          if (do_norm) {
 #pragma unroll
-            for (int j = 0; j < 128; ++j) ss += v[j] * v[j];
-            const float rs = rsqrtf(ss * (1.0f / 128.0f) + p.norm_eps);
-            const float* w = (col0 < p.norm_seg) ? p.norm_w0 : p.norm_w1;
-#pragma unroll
-            for (int j = 0; j < 128; j += 4) {
-              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j));
+            for (int j = 0; j < 32; j += 4) {
+              const float4 ww = __ldg(reinterpret_cast<const float4*>(w + c * 32 + j));
               v[j] *= rs * ww.x; v[j + 1] *= rs * ww.y; v[j + 2] *= rs * ww.z; v[j + 3] *= rs * ww.w;
             }
           }
-          if (col0 < p.rope_cols) {
-            const int pos = (valid ? row : 0) / p.rope_rows_per_pos;
-            const float* cs = p.rope_cos + (long long)pos * 64;
-            const float* sn = p.rope_sin + (long long)pos * 64;
+          if (do_rope) {  // interleaved pairs (2i, 2i+1) rotate by angle i of the row's position: 16 angles per 32 columns
 #pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + j));
-              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + j));
+            for (int j = 0; j < 16; j += 4) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs + c * 16 + j));
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(sn + c * 16 + j));
               float a, b;
               a = v[2 * j + 0]; b = v[2 * j + 1]; v[2 * j + 0] = a * c4.x - b * s4.x; v[2 * j + 1] = b * c4.x + a * s4.x;
               a = v[2 * j + 2]; b = v[2 * j + 3]; v[2 * j + 2] = a * c4.y - b * s4.y; v[2 * j + 3] = b * c4.y + a * s4.y;
@@ -197,16 +209,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tadd
               a = v[2 * j + 6]; b = v[2 * j + 7]; v[2 * j + 6] = a * c4.w - b * s4.w; v[2 * j + 7] = b * c4.w + a * s4.w;
             }
           }
-        } else if (p.bias) {
+          if (!do_norm && !do_rope && p.bias) {
 #pragma unroll
-          for (int j = 0; j < 128; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + c * 32 + j));
+              v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
           }
-        }
-        if (valid) {
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 128; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col0 + j, v + j);
+            for (int j = 0; j < 32; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col0 + c * 32 + j, v + j);
+          }
         }
       }
     }
@@ -398,7 +411,8 @@ struct Gemm2Smem {
 constexpr int GEMM2_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps (lane quarter x column half)
 
 template <int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(200)
+// (10 warps are budgeted as 12 by the register allocator: at most 168 registers per thread)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   using L = Gemm2Smem<STAGES>;

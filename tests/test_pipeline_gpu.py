@@ -158,5 +158,8 @@ def test_actionmesh_b200_pipeline_call_end_to_end(amb_lib):
         _, vb = direct(VideoInput(list(frames), ts), anchor_latent, pts, torch.nn.functional.normalize(pts, dim=-1), seed=44)
         ref_v, ref_t = vb.get_ordered()
         assert ref_t.tolist() == ts.tolist()
-        for m, v in zip(meshes, ref_v):
-            assert np.array_equal(m.vertices, v.cpu().numpy())
+        for i, (m, v) in enumerate(zip(meshes, ref_v)):
+            if i < 16:   # first Stage-II window: same kernels, same inputs => bit-identical
+                assert np.array_equal(m.vertices, v.cpu().numpy()), i
+            else:        # later windows start from normals accumulated with float atomics (index_add_): order noise only
+                assert np.allclose(m.vertices, v.cpu().numpy(), atol=1e-4), i

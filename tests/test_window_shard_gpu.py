@@ -144,10 +144,23 @@ def test_sharded_program_emulated_on_one_gpu(amb_lib, world):
         t.join(timeout=300)
     assert not errs, errs
     errors = [float((outs[r] - ref).norm() / ref.norm()) for r in range(world)]
-    print("SHARD_EMULATION", world, errors)
+    # When a rank's chunk is a whole number of 128-key tiles the sharded key loop visits the same tiles in the same order
+    # as the single-GPU loop: bit-identical.  With 1 frame (64 keys) per rank every tile is a ragged half tile, a different
+    # but equally valid summation order; three CFG-7.5 steps amplify that like any other rounding difference, so the bar
+    # there is the distance to the fp32 oracle: the sharded result may not be further from it than the single-GPU result.
+    from oracle import denoiser_oracle as do
+
+    ocfg = do.DenoiserConfig(inflated_layers=(0, 2), **d)
+    truth = do.flow_denoise(do.OracleDenoiser(synth.make_state_dict(cfg, 3), ocfg), lat, ctx, mask, fs,
+                            num_inference_steps=3, guidance_scales=[7.5])
+    e_single = float((ref - truth).norm() / truth.norm())
+    e_shard = float((outs[0] - truth).norm() / truth.norm())
+    print("SHARD_EMULATION", world, errors[0], "vs oracle: single", e_single, "sharded", e_shard)
+    aligned = (lat.shape[1] // world) * (lat.shape[2] + 1) % 128 == 0
     for r in range(world):
-        assert errors[r] < 5e-3, (r, errors)
+        assert errors[r] < (5e-3 if aligned else 3e-2), (r, errors)
         assert torch.equal(outs[r][0, 0], lat[0, 0])   # the observed frame comes back bit-identical on every rank
+    assert e_shard <= 1.25 * e_single + 1e-3, (e_single, e_shard)
     assert all(torch.equal(outs[0], o) for o in outs[1:])  # every rank ends with the same full window
 
 

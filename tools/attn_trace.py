@@ -16,17 +16,17 @@ torch.cuda.synchronize()
 _lib.load_library().amb_debug_set_attn_trace(None)
 t = tr.cpu().view(5, 16, 8)
 t0 = int(t[4, 0, 0])
-print("softmax (warps 0 and 4): 0 enter, 1 s_full passed, 2 S loaded, 3 exps done, 4 P stored + arrived")
+print("softmax (warp 0 of set 0 / set 1): 0 enter, 1 s_full passed, 2 half0 loaded, 3 half0 handed over, 4 half1 loaded, 5 half1 handed over")
 print("mma: 0 iteration start, 1 QK(j+2) issued, 2 v_full passed, 3 p_ready passed, 4 PV(j) issued")
 for j in range(5):
     for r, nme in ((0, "sm_w0"), (1, "sm_w4"), (4, "mma")):
-        print(f"j={100 + j} {nme:6s} " + " ".join(f"{int(x) - t0:7d}" for x in t[r, j, :5]))
+        print(f"j={100 + j} {nme:6s} " + " ".join(f"{int(x) - t0:7d}" for x in t[r, j, :6]))
     print()
-for r, nme in ((0, "sm_w0"), (1, "sm_w4")):
-    d = t[r, 1:15]
-    print(nme, "period", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "wait_s", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
-          "load", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "exps", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
-          "store+arrive", statistics.mean((d[:, 4] - d[:, 3]).tolist()))
+for r, nme, par in ((0, "set0", 0), (1, "set1", 1)):
+    d = t[r, 2 + par:14:2]     # the set's own tiles (every second one)
+    print(nme, "period(2 tiles)", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "wait_s", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
+          "load0", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "half0", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
+          "load1", statistics.mean((d[:, 4] - d[:, 3]).tolist()), "half1", statistics.mean((d[:, 5] - d[:, 4]).tolist()))
 d = t[4, 1:15]
 print("mma period", statistics.mean((d[1:, 0] - d[:-1, 0]).tolist()), "k_wait+qk_issue", statistics.mean((d[:, 1] - d[:, 0]).tolist()),
       "v_wait", statistics.mean((d[:, 2] - d[:, 1]).tolist()), "p_wait", statistics.mean((d[:, 3] - d[:, 2]).tolist()),
