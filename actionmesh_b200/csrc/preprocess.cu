@@ -90,7 +90,116 @@ static int grid_for_items(long long items, int block) {
 
 using namespace amb;
 
+// ---- ImagePreprocessor (actionmesh/preprocessing/image_processor.py:26-146): RGBA frames -> composite on white -> crop to
+// the foreground bounding box -> pad to a square with a margin.  Two kernels around a few host integers (the bounding boxes):
+// alpha statistics, then composite + crop + pad straight to the uint8 image the reference hands on as PIL.
+
+// per image: stats[0..3] = xmin, ymin, xmax, ymax of alpha > 0 (image_processor.py:57-64), stats[4] = count of alpha > 127
+// (is_valid_alpha, :15-23).  One warp-aggregated atomic per row segment; stats are initialised by alpha_stats_init_kernel.
+__global__ void alpha_stats_init_kernel(int32_t* stats, int n, int h, int w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    stats[5 * i + 0] = w;
+    stats[5 * i + 1] = h;
+    stats[5 * i + 2] = -1;
+    stats[5 * i + 3] = -1;
+    stats[5 * i + 4] = 0;
+  }
+}
+__global__ void __launch_bounds__(256) alpha_stats_kernel(const uint8_t* __restrict__ rgba, int h, int w, int32_t* stats) {
+  const int img = blockIdx.z;
+  const int y = blockIdx.y;
+  const uint8_t* row = rgba + (((long long)img * h + y) * w) * 4;
+  int xmin = w, xmax = -1, fg = 0;
+  for (int x = blockIdx.x * blockDim.x + threadIdx.x; x < w; x += gridDim.x * blockDim.x) {
+    const int a = row[4 * x + 3];
+    if (a > 0) {
+      xmin = min(xmin, x);
+      xmax = max(xmax, x);
+    }
+    fg += a > 127;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+    fg += __shfl_xor_sync(0xffffffffu, fg, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    int32_t* st = stats + 5 * img;
+    if (xmax >= 0) {
+      atomicMin(st + 0, xmin);
+      atomicMax(st + 2, xmax);
+      atomicMin(st + 1, y);
+      atomicMax(st + 3, y);
+    }
+    if (fg) atomicAdd(st + 4, fg);
+  }
+}
+
+// out (n, bh + 2 pad_y, bw + 2 pad_x, 3) u8: inside the box the composite rgb*a + 1*(1-a) in the reference's float32
+// operation order (image_processor.py:44-52: (rgb*f32(1/255))*alpha + bg*(1-alpha), alpha = a*f32(1/255)), then *255 and
+// truncation like `(img * 255).astype(np.uint8)` (:143-145); the padding is the background value 1.0 -> 255.
+__global__ void __launch_bounds__(256) composite_crop_pad_kernel(const uint8_t* __restrict__ rgba, int h, int w, int bx, int by,
+                                                                 int bw, int bh, int pad_x, int pad_y, uint8_t* __restrict__ out,
+                                                                 long long total) {
+  const int ow = bw + 2 * pad_x, oh = bh + 2 * pad_y;
+  const float k = 1.0f / 255.0f;  // numpy multiplies the float32 array by float32(1.0 / 255.0)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % ow);
+    const long long t = i / ow;
+    const int oy = (int)(t % oh);
+    const long long img = t / oh;
+    uint8_t r = 255, g = 255, b = 255;
+    const int sx = ox - pad_x, sy = oy - pad_y;
+    if (sx >= 0 && sx < bw && sy >= 0 && sy < bh) {
+      const uint8_t* px = rgba + ((img * h + (by + sy)) * w + (bx + sx)) * 4;
+      const float a = __fmul_rn((float)px[3], k);
+      const float bgw = __fmul_rn(1.0f, __fsub_rn(1.0f, a));
+      const float c0 = __fadd_rn(__fmul_rn(__fmul_rn((float)px[0], k), a), bgw);
+      const float c1 = __fadd_rn(__fmul_rn(__fmul_rn((float)px[1], k), a), bgw);
+      const float c2 = __fadd_rn(__fmul_rn(__fmul_rn((float)px[2], k), a), bgw);
+      r = (uint8_t)(int)__fmul_rn(c0, 255.0f);
+      g = (uint8_t)(int)__fmul_rn(c1, 255.0f);
+      b = (uint8_t)(int)__fmul_rn(c2, 255.0f);
+    }
+    uint8_t* d = out + i * 3;
+    d[0] = r;
+    d[1] = g;
+    d[2] = b;
+  }
+}
+
 extern "C" {
+
+int amb_alpha_stats(const uint8_t* rgba, int n_images, int height, int width, int32_t* stats, amb_stream_t stream) {
+  AMB_CHECK_ARG(rgba && stats, "alpha_stats: null pointer");
+  AMB_CHECK_ARG(height > 0 && width > 0 && height <= 65535, "alpha_stats: bad geometry %dx%d", height, width);
+  if (n_images <= 0) return AMB_OK;
+  AMB_CHECK_ARG(n_images <= 65535, "alpha_stats: at most 65535 images per call");
+  cudaStream_t s = (cudaStream_t)stream;
+  alpha_stats_init_kernel<<<(n_images + 127) / 128, 128, 0, s>>>(stats, n_images, height, width);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  dim3 grid((width + 255) / 256 > 4 ? 4 : (width + 255) / 256, height, n_images);
+  alpha_stats_kernel<<<grid, 256, 0, s>>>(rgba, height, width, stats);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
+
+int amb_composite_crop_pad(const uint8_t* rgba, int n_images, int height, int width, int box_x, int box_y, int box_w, int box_h,
+                           int pad_x, int pad_y, uint8_t* out, amb_stream_t stream) {
+  AMB_CHECK_ARG(rgba && out, "composite_crop_pad: null pointer");
+  AMB_CHECK_ARG(height > 0 && width > 0 && box_w > 0 && box_h > 0 && box_x >= 0 && box_y >= 0 && box_x + box_w <= width &&
+                    box_y + box_h <= height && pad_x >= 0 && pad_y >= 0,
+                "composite_crop_pad: box (%d,%d,%d,%d) / padding (%d,%d) do not fit the %dx%d image", box_x, box_y, box_w, box_h,
+                pad_x, pad_y, height, width);
+  if (n_images <= 0) return AMB_OK;
+  const long long total = (long long)n_images * (box_h + 2 * pad_y) * (box_w + 2 * pad_x);
+  composite_crop_pad_kernel<<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(rgba, height, width, box_x, box_y, box_w,
+                                                                                         box_h, pad_x, pad_y, out, total);
+  AMB_CHECK_CUDA(cudaGetLastError());
+  return AMB_OK;
+}
 
 int amb_resize_h_u8(const uint8_t* src, int n_images, int in_h, int in_w, int channels_in, int y0, int n_rows,
                     const int32_t* bounds, const int32_t* coeffs, int ksize, int out_w, uint8_t* dst, amb_stream_t stream) {

@@ -242,6 +242,34 @@ def resize_v_normalize(src: torch.Tensor, y0: int, bounds: torch.Tensor, coeffs:
     return out
 
 
+def alpha_stats(rgba: torch.Tensor) -> torch.Tensor:
+    """(n, H, W, 4) u8 RGBA frames -> (n, 5) int32: xmin, ymin, xmax, ymax of alpha > 0 and the count of alpha > 127."""
+    global launch_count
+    _need(rgba, torch.uint8, "rgba")
+    assert rgba.dim() == 4 and rgba.shape[3] == 4 and rgba.is_contiguous()
+    n, H, W, _ = rgba.shape
+    stats = torch.empty(n, 5, dtype=torch.int32, device=rgba.device)
+    rc = _lib.load_library().amb_alpha_stats(rgba.data_ptr(), n, H, W, stats.data_ptr(), _stream())
+    _lib.check(rc, "amb_alpha_stats")
+    launch_count += 2
+    return stats
+
+
+def composite_crop_pad(rgba: torch.Tensor, box: tuple, pad_x: int, pad_y: int) -> torch.Tensor:
+    """RGBA frames -> white-composited, cropped to box = (x, y, w, h), padded uint8 RGB frames (n, h + 2 pad_y, w + 2 pad_x, 3)."""
+    global launch_count
+    _need(rgba, torch.uint8, "rgba")
+    assert rgba.dim() == 4 and rgba.shape[3] == 4 and rgba.is_contiguous()
+    n, H, W, _ = rgba.shape
+    x, y, w, h = (int(v) for v in box)
+    out = torch.empty(n, h + 2 * pad_y, w + 2 * pad_x, 3, dtype=torch.uint8, device=rgba.device)
+    rc = _lib.load_library().amb_composite_crop_pad(rgba.data_ptr(), n, H, W, x, y, w, h, int(pad_x), int(pad_y),
+                                                    out.data_ptr(), _stream())
+    _lib.check(rc, "amb_composite_crop_pad")
+    launch_count += 1
+    return out
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global launch_count
     _need(src, torch.float32, "src")

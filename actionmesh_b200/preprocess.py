@@ -168,3 +168,59 @@ class B200ImagePreprocessor:
             for j, i in enumerate(idx):
                 out[i] = pv[j]
         return torch.stack(out) if len(groups) > 1 else pv
+
+
+class B200FramePreprocessor:
+    """`ImagePreprocessor` (actionmesh/preprocessing/image_processor.py:104-146) on the GPU: RGBA frames are composited on a
+    white background, cropped to the foreground bounding box (shared across the clip unless `independent_cropping`) and padded
+    to a square with a `padding_ratio` margin.  Same constructor fields, same `process_images(frames) -> list[PIL.Image]`, same
+    ValueError for frames without a usable alpha channel; `process_to_u8` keeps the result on the device for the encoder.
+
+    Two kernels (amb_alpha_stats, amb_composite_crop_pad) around the host integers the reference computes too (bounding boxes,
+    paddings, image_processor.py:57-101); the uint8 output is bit-identical to the reference's."""
+
+    def __init__(self, independent_cropping: bool = False, padding_ratio: float = 0.1, device="cuda"):
+        self.independent_cropping = independent_cropping
+        self.padding_ratio = padding_ratio
+        self.bg_color = np.array([1.0, 1.0, 1.0])
+        self.device = torch.device(device)
+
+    @staticmethod
+    def _padding(w: int, h: int, padding_ratio: float):
+        max_dim = max(w, h)                                 # apply_padding, image_processor.py:91-96
+        pad_base = int(max_dim * padding_ratio)
+        return pad_base + (max_dim - w) // 2, pad_base + (max_dim - h) // 2
+
+    def process_to_u8(self, frames: List) -> List[torch.Tensor]:
+        """-> one (H', W', 3) uint8 CUDA tensor per frame (all the same size unless independent_cropping)."""
+        if self.device.type != "cuda":
+            raise AmbError("B200FramePreprocessor only runs on a CUDA (sm_100) device; there is no CPU path")
+        arrs = [np.ascontiguousarray(f if getattr(f, "mode", "RGBA") == "RGBA" else f.convert("RGBA")) for f in frames]
+        if len({a.shape for a in arrs}) != 1:
+            raise AmbError("B200FramePreprocessor: all frames of a clip must have the same size")
+        with torch.cuda.device(self.device):
+            rgba = torch.from_numpy(np.stack(arrs)).pin_memory().to(self.device, non_blocking=True)
+            n, H, W, _ = rgba.shape
+            stats = ops.alpha_stats(rgba).cpu().tolist()     # 5 integers per frame: the one host round trip of the stage
+            min_count = int(H * W * 0.01)                     # is_valid_alpha(min_ratio=0.01, threshold=127), :15-23
+            boxes = []
+            for xmin, ymin, xmax, ymax, fg in stats:
+                if not (H * W - fg >= min_count and fg >= min_count):
+                    raise ValueError("Invalid alpha channel: insufficient foreground/background")
+                boxes.append((xmin, ymin, xmax - xmin + 1, ymax - ymin + 1))
+            if not self.independent_cropping:                # aggregate_bboxes, :69-77
+                x0, y0 = min(b[0] for b in boxes), min(b[1] for b in boxes)
+                x1, y1 = max(b[0] + b[2] for b in boxes), max(b[1] + b[3] for b in boxes)
+                box = (x0, y0, x1 - x0, y1 - y0)
+                px, py = self._padding(box[2], box[3], self.padding_ratio)
+                return list(ops.composite_crop_pad(rgba, box, px, py))
+            out = []
+            for i, box in enumerate(boxes):
+                px, py = self._padding(box[2], box[3], self.padding_ratio)
+                out.append(ops.composite_crop_pad(rgba[i:i + 1], box, px, py)[0])
+            return out
+
+    def process_images(self, frames: List) -> List:
+        from PIL import Image
+
+        return [Image.fromarray(t.cpu().numpy()) for t in self.process_to_u8(frames)]

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 9
+#define AMB_ABI_VERSION 10
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -85,6 +85,19 @@ int amb_resize_h_u8(const uint8_t* src, int n_images, int in_h, int in_w, int ch
 int amb_resize_v_normalize(const uint8_t* src, int n_images, int n_rows, int y0, int out_w, const int32_t* bounds,
                            const int32_t* coeffs, int ksize, int out_h, const float* lut256, const float* mean3_host,
                            const float* std3_host, float* dst, uint8_t* dst_u8, amb_stream_t stream);
+
+/* ---- frame preprocessing before the encoders (second half) -------------------------------------------
+ * Replaces the host numpy/PIL arithmetic of ImagePreprocessor.process_images (actionmesh/preprocessing/image_processor.py:
+ * 26-146): RGBA frames are composited on a white background, cropped to the (shared or per-frame) foreground bounding box
+ * and padded to a square with a margin.
+ *  alpha_stats: rgba (n, h, w, 4) u8 -> stats (n, 5) int32 = xmin, ymin, xmax, ymax of alpha > 0 (:57-64; xmax = -1 when the
+ *    frame is fully transparent) and the number of pixels with alpha > 127 (is_valid_alpha, :15-23).
+ *  composite_crop_pad: -> out (n, box_h + 2 pad_y, box_w + 2 pad_x, 3) u8.  Inside the box: the float32 composite of :44-52 in
+ *    the reference's operation order, times 255, truncated like `(img * 255).astype(uint8)` (:143-145); outside: 255.
+ *    The uint8 result is bit-identical to the reference's PIL output. */
+int amb_alpha_stats(const uint8_t* rgba, int n_images, int height, int width, int32_t* stats, amb_stream_t stream);
+int amb_composite_crop_pad(const uint8_t* rgba, int n_images, int height, int width, int box_x, int box_y, int box_w, int box_h,
+                           int pad_x, int pad_y, uint8_t* out, amb_stream_t stream);
 
 /* ---- Stage II (temporal autoencoder) helpers — first "next" row of SURVEY 8(f) -----------------------------------------
  * alpha_rows: the (source_alpha, target_alpha) token of actionmesh/model/temporal_autoencoder.py:233-237 (TimestepEmbedder,

@@ -100,3 +100,38 @@ def bit_preprocess_pil(images, shortest_edge=256, crop=(224, 224), rescale=1 / 2
         u8s.append(c)
     pv = np.stack(outs).astype(np.float32)
     return (pv, np.stack(u8s)) if return_u8 else pv
+
+
+# ---- ImagePreprocessor (actionmesh/preprocessing/image_processor.py:26-146) restated with numpy only ------------------------
+def frame_preprocess(frames_rgba, independent_cropping: bool = False, padding_ratio: float = 0.1):
+    """frames_rgba: list of (H, W, 4) uint8 arrays -> list of (H', W', 3) uint8 arrays, following load_image (:26-66),
+    aggregate_bboxes (:69-77), apply_padding (:80-101) and the uint8 conversion of process_images (:142-146)."""
+    import numpy as np
+
+    bg = np.array([1.0, 1.0, 1.0]).astype(np.float32)
+    comps, boxes = [], []
+    for img in frames_rgba:
+        rgb, alpha = img[..., :3], img[..., 3]
+        total = alpha.size
+        min_count = int(total * 0.01)
+        fg = np.count_nonzero(alpha > 127)
+        if not (total - fg >= min_count and fg >= min_count):
+            raise ValueError("Invalid alpha channel: insufficient foreground/background")
+        a = (alpha.astype(np.float32) * (1.0 / 255.0))[..., None]
+        comps.append(rgb.astype(np.float32) * (1.0 / 255.0) * a + bg * (1.0 - a))
+        mask = alpha > 0
+        rows, cols = np.nonzero(mask.any(axis=1))[0], np.nonzero(mask.any(axis=0))[0]
+        boxes.append((cols[0], rows[0], cols[-1] - cols[0] + 1, rows[-1] - rows[0] + 1))
+    if not independent_cropping:
+        x0, y0 = min(b[0] for b in boxes), min(b[1] for b in boxes)
+        x1, y1 = max(b[0] + b[2] for b in boxes), max(b[1] + b[3] for b in boxes)
+        boxes = [(x0, y0, x1 - x0, y1 - y0)] * len(boxes)
+    out = []
+    for comp, (x, y, w, h) in zip(comps, boxes):
+        crop = comp[y:y + h, x:x + w]
+        m = max(w, h)
+        pb = int(m * padding_ratio)
+        px, py = pb + (m - w) // 2, pb + (m - h) // 2
+        padded = np.pad(crop, ((py, py), (px, px), (0, 0)), mode="constant", constant_values=1.0)
+        out.append((padded * np.float32(255)).astype(np.uint8))
+    return out
