@@ -270,6 +270,23 @@ def composite_crop_pad(rgba: torch.Tensor, box: tuple, pad_x: int, pad_y: int) -
     return out
 
 
+def nearest_neighbors(query: torch.Tensor, reference: torch.Tensor, want_index: bool = True):
+    """(Q, 3), (R, 3) fp32 CUDA points -> (distance (Q,) fp32, index (Q,) int32) of each query's nearest reference point."""
+    global launch_count
+    _need(query, torch.float32, "query")
+    _need(reference, torch.float32, "reference")
+    assert query.dim() == 2 and query.shape[1] == 3 and reference.dim() == 2 and reference.shape[1] == 3
+    q, r = query.contiguous(), reference.contiguous()
+    dist = torch.empty(q.shape[0], dtype=torch.float32, device=q.device)
+    idx = torch.empty(q.shape[0], dtype=torch.int32, device=q.device) if want_index else None
+    scratch = torch.empty(q.shape[0], dtype=torch.int64, device=q.device)
+    rc = _lib.load_library().amb_nearest_neighbors(q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0], scratch.data_ptr(),
+                                                   dist.data_ptr(), _ptr(idx), _stream())
+    _lib.check(rc, "amb_nearest_neighbors")
+    launch_count += 3
+    return dist, idx
+
+
 def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     global launch_count
     _need(src, torch.float32, "src")

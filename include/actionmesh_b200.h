@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 10
+#define AMB_ABI_VERSION 11
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -98,6 +98,13 @@ int amb_resize_v_normalize(const uint8_t* src, int n_images, int n_rows, int y0,
 int amb_alpha_stats(const uint8_t* rgba, int n_images, int height, int width, int32_t* stats, amb_stream_t stream);
 int amb_composite_crop_pad(const uint8_t* rgba, int n_images, int height, int width, int box_x, int box_y, int box_w, int box_h,
                            int pad_x, int pad_y, uint8_t* out, amb_stream_t stream);
+
+/* ---- ActionBench evaluation ----------------------------------------------------------------------
+ * Replaces scipy's KDTree.query at actionbench/chamfer.py:44-50,78-82: for each of n_query points (xyz fp32, row-major) the
+ * Euclidean distance to and the index of its nearest point among n_reference points.  scratch_u64: n_query * 8 bytes of
+ * device memory; out_dist / out_index: either may be NULL.  Ties resolve to the lowest index. */
+int amb_nearest_neighbors(const float* query, int n_query, const float* reference, int n_reference, void* scratch_u64,
+                          float* out_dist, int32_t* out_index, amb_stream_t stream);
 
 /* ---- Stage II (temporal autoencoder) helpers — first "next" row of SURVEY 8(f) -----------------------------------------
  * alpha_rows: the (source_alpha, target_alpha) token of actionmesh/model/temporal_autoencoder.py:233-237 (TimestepEmbedder,
