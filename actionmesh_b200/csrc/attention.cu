@@ -747,8 +747,11 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
   AMB_CHECK_ARG(a->batch <= 65535 && a->heads <= 65535, "flash_attn: grid limits");
   cudaStream_t s = (cudaStream_t)stream;
   if (a->head_dim == 64) return launch_attn_v1<64, 4>(a, s);
-  // development switch (A/B against the previous product kernel); the pair kernel is the product path
-  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 6; }();
-  if (ver == 4) return launch_attn_v4(a, s);
+  // head_dim 128: the CTA-pair kernel for long key loops (its two softmax sets, three S buffers and the fix-up pass pay off
+  // from a few dozen key tiles on: the inflated self-attention, 257 tiles); the single-CTA kernel for short ones (the
+  // per-frame cross-attention to 257 context tokens = 3 tiles).  AMB_ATTN_VER (development): 4 / 6 force one kernel.
+  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 0; }();
+  const int key_tiles = (a->sk + 127) / 128;
+  if (ver == 4 || (ver == 0 && key_tiles < 48)) return launch_attn_v4(a, s);
   return launch_attn_pair(a, g_attn_trace, s);
 }
