@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libactionmesh_b200.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 EXPORTS = [
     "amb_last_error", "amb_abi_version", "amb_device_info", "amb_cfg_euler_step", "amb_layernorm",
@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("norm_w0", C.c_void_p), ("norm_w1", C.c_void_p), ("norm_eps", C.c_float),
         ("rope_cols", C.c_int32), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_rows_per_pos", C.c_int32),
+        ("c2", C.c_void_p), ("ldc2", C.c_int64),
     ]
 
 

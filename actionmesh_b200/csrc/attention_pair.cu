@@ -72,10 +72,10 @@ __host__ __device__ constexpr bool pa_emulated(int emu, int g, int r) {
   return emu == 0 ? false : emu == 1 ? (r == 0 && (g & 1) == 0) : emu == 2 ? (((g + r) & 1) == 0) : !(r == 1 && (g & 1) == 1);
 }
 
-enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };
+enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact on dirty units only / two-set fast path
 #ifndef AMB_ATTN_TRACE
 #define AMB_ATTN_TRACE 0  // 1: compile the clock64 role timeline (tools/attn_trace.py) into the kernels; off in the product build
-#endif  // MODE: exact / exact on dirty units only / two-set fast path
+#endif
 
 template <int KS, int VS, int EMU, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PA_THREADS, 1)
@@ -275,13 +275,11 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float l_a = 0.f, l_b = 0.f;  // partial row sums: my 32 keys of every tile of my set
     bool dirty = false;
 
-    // One half step: the 32 scores already in `s` (keys [64 h, 64 h + 64) of tile j) -> bf16 P in TMEM, handed to the MMA
-    // warp.  The TMEM load of the NEXT half step is issued into the same registers as soon as the exponentials are done
-    // (before the P store and hand-over), so its latency hides behind them.
-    float s[32];  // s[4g + {0,1}] = row_a, keys 64 h + 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
-    auto half_step = [&](int j, int buf, int h, bool masked, bool more) {
+    auto half_step = [&](int j, int buf, int h, bool masked) {
       const bool tr = tracer && j >= 100 && j < 116;
       const uint32_t s_addr = tmem_base + buf * 128 + h * 64 + lane_sel;
+      float s[32];  // s[4g + {0,1}] = row_a, keys 64 h + 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
+      tmem_ld16_256b_x8f(s_addr, s);
       tmem_wait_ld();
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 2 + 2 * h] = clock64();
       uint32_t pk[16];
@@ -315,19 +313,6 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         pk[2 * g] = pack_bf16(ea0, ea1);
         pk[2 * g + 1] = pack_bf16(eb0, eb1);
       }
-      // ---- prefetch: the other half of this tile, or the first half of my next tile when its S is already complete
-      bool prefetched = false;
-      if (h == 0) {
-        tmem_ld16_256b_x8f(s_addr + 64, s);
-        prefetched = true;
-      } else if (more) {
-        const int jn = j + 2, nbuf = jn % PA_NBUF;
-        if (__all_sync(0xffffffffu, mbar_try_wait(&s_full[nbuf], (jn / PA_NBUF) & 1))) {  // one decision per warp
-          tc_fence_after();
-          tmem_ld16_256b_x8f(tmem_base + nbuf * 128 + lane_sel, s);
-          prefetched = true;
-        }
-      }
       float x0, x1, y0, y1;
       upk2(sum_a, x0, x1);
       upk2(sum_b, y0, y1);
@@ -346,26 +331,23 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         else mbar_arrive_remote(bar, 0);
       }
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 3 + 2 * h] = clock64();
-      return prefetched;
     };
 
-    bool have = false;  // the first half of the current tile is already on its way into `s`
     for (int j = set; j < n_kv; j += 2) {
       const int buf = j % PA_NBUF;
       const uint32_t bph = (j / PA_NBUF) & 1;
       const bool masked = has_tail && (j % tiles_per_chunk == tiles_per_chunk - 1);
       const bool tr = tracer && j >= 100 && j < 116;
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 0] = clock64();
-      if (!have) {
-        mbar_wait(&s_full[buf], bph);
-        tc_fence_after();
-      }
+      mbar_wait(&s_full[buf], bph);
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 1] = clock64();
+      tc_fence_after();
       if (j == 0) {
         // set 0 anchors every row's reference maximum on tile 0 and publishes it to set 1
         float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
+          float s[32];
           tmem_ld16_256b_x8f(tmem_base + h * 64 + lane_sel, s);
           tmem_wait_ld();
 #pragma unroll
@@ -397,9 +379,8 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         m_a = xch[row_a];
         m_b = xch[row_a + 8];
       }
-      if (!have) tmem_ld16_256b_x8f(tmem_base + buf * 128 + lane_sel, s);
-      half_step(j, buf, 0, masked, false);
-      have = half_step(j, buf, 1, masked, j + 2 < n_kv);
+      half_step(j, buf, 0, masked);
+      half_step(j, buf, 1, masked);
     }
     if (__any_sync(0xffffffffu, dirty) && lane == 0) atomicOr(p.dirty + unit, 1);
 

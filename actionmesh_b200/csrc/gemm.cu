@@ -38,6 +38,8 @@ struct GemmParams {
   const float* rope_cos;
   const float* rope_sin;
   int rope_rows_per_pos;
+  void* C2;        // optional bf16 copy of the output
+  long long ldc2;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -140,6 +142,10 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
     add_res32(p, *res, v);
 #pragma unroll
     for (int j = 0; j < NV; j += 8) store8(p.C, p.c_fp32, drow * p.ldc + col + j, v + j);
+    if (p.C2) {
+#pragma unroll
+      for (int j = 0; j < NV; j += 8) store8(p.C2, 0, drow * p.ldc2 + col + j, v + j);
+    }
     return;
   }
 #pragma unroll
@@ -151,6 +157,7 @@ __device__ __forceinline__ void finish_and_store(const GemmParams& p, float* v, 
       for (int t = 0; t < 8; ++t) v[j + t] += r[t];
     }
     store8(p.C, p.c_fp32, drow * p.ldc + col + j, v + j);
+    if (p.C2) store8(p.C2, 0, drow * p.ldc2 + col + j, v + j);
   }
 }
 
@@ -386,6 +393,7 @@ static GemmParams make_params(const amb_gemm_args* a) {
   p.norm_eps = a->norm_eps;
   p.rope_cols = a->rope_cols; p.rope_cos = a->rope_cos; p.rope_sin = a->rope_sin;
   p.rope_rows_per_pos = a->rope_rows_per_pos > 0 ? a->rope_rows_per_pos : 1;
+  p.C2 = a->c2; p.ldc2 = a->ldc2;
 
   return p;
 }
@@ -650,12 +658,13 @@ extern "C" int amb_gemm_bf16(const amb_gemm_args* a, amb_stream_t stream) {
                 "gemm: bad k_split %d", a->k_split);
   AMB_CHECK_ARG(!a->residual || a->ldr % 8 == 0, "gemm: ldr must be a multiple of 8");
   AMB_CHECK_ARG(a->act == 0 || a->act == 1, "gemm: unknown activation %d", a->act);
+  AMB_CHECK_ARG(!a->c2 || a->ldc2 % 8 == 0, "gemm: ldc2 must be a multiple of 8");
   if (a->norm_cols > 0 || a->rope_cols > 0) {
     AMB_CHECK_ARG(a->n % 128 == 0 && a->norm_cols % 128 == 0 && a->rope_cols % 128 == 0,
                   "gemm: head epilogue needs n, norm_cols, rope_cols multiples of 128");
     AMB_CHECK_ARG(a->norm_cols == 0 || (a->norm_w0 && a->norm_seg % 128 == 0), "gemm: norm weights / norm_seg (multiple of 128) required");
     AMB_CHECK_ARG(a->rope_cols == 0 || (a->rope_cos && a->rope_sin), "gemm: rope tables required");
-    AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale, "gemm: head epilogue excludes residual/activation/col_scale");
+    AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale && !a->c2, "gemm: head epilogue excludes residual/activation/col_scale/c2");
   }
   cudaStream_t s = (cudaStream_t)stream;
   static const int two_cta = []() { const char* e = getenv("AMB_GEMM_2CTA"); return e ? atoi(e) : 1; }();  // 2-CTA kernel is the product path for N % 256 == 0

@@ -171,6 +171,7 @@ class B200Denoiser:
         rows = slice(b0 * TL, (b0 + nb) * TL)
         scale = 1.0 / math.sqrt(dh)
         h, xn, tmp = ws["h"][rows], ws["xn"][rows], ws["tmp"][rows]
+        hb = ws["hb"][rows] if f32 else None
         qkv, att, ff = ws["qkv"][rows], ws["att"][rows], ws["ff"][rows]
         rope_cos, rope_sin = st.rope_cos[b0 * T:(b0 + nb) * T], st.rope_sin[b0 * T:(b0 + nb) * T]
         skips = [sk[rows] for sk in ws["skips"]]
@@ -186,10 +187,8 @@ class B200Denoiser:
             p = f"blocks.{i}."
             if i > half:  # block.py:131-133: LN(W_skip [skip | h] + b) without materialising the concat
                 sp -= 1
-                a2 = h_in
-                if f32:
-                    a2 = ops.cast_bf16(h_in, out=xn)  # bf16 GEMM operand of the fp32 stream (xn is free here)
-                ops.gemm(skips[sp], w[p + "skip.w"], tmp, a2=a2, bias=w[p + "skip.b"])
+                # fp32 stream: its bf16 GEMM-operand copy was written by the previous block's last GEMM (second output)
+                ops.gemm(skips[sp], w[p + "skip.w"], tmp, a2=hb if f32 else h_in, bias=w[p + "skip.b"])
                 ops.layernorm(tmp, w[p + "norm_skip.g"], w[p + "norm_skip.b"], 1e-5, out=h)
                 h_in = h
             # ---- self-attention (block.py:137-142, attention_processor.py:49-166)
@@ -241,9 +240,11 @@ class B200Denoiser:
                 h_in = skips[sp]
                 sp += 1
             else:
-                ops.gemm(ff, w[p + "ff2.w"], h, bias=w[p + "ff2.b"], residual=h)
+                # fp32 stream: the stream stays in h; the second (bf16) output is the operand `linear_skip(cat[skip, h])`
+                # needs — the skip itself for a pushing block, the h half for the block before a popping one
+                copy = skips[sp] if i < half else (hb if (f32 and half <= i < c.num_layers - 1) else None)
+                ops.gemm(ff, w[p + "ff2.w"], h, bias=w[p + "ff2.b"], residual=h, out2=copy)
                 if i < half:
-                    ops.cast_bf16(h, out=skips[sp])
                     sp += 1
         assert h_in is h  # the last block is never a pushing block: its output lives in ws['h'] for the output head
 
@@ -361,6 +362,7 @@ class B200Denoiser:
             "h": torch.empty(M, c.width, dtype=hd, device=dev),
             "xn": torch.empty(M, c.width, dtype=bf, device=dev),
             "tmp": torch.empty(M, c.width, dtype=hd, device=dev),
+            "hb": torch.empty(M, c.width, dtype=bf, device=dev) if self.residual_fp32 else None,
             "qkv": torch.empty(M, 3 * c.width, dtype=bf, device=dev),
             "att": torch.empty(M, c.width, dtype=bf, device=dev),
             "ff": torch.empty(M, c.ff_dim, dtype=bf, device=dev),

@@ -333,7 +333,7 @@ def add_bias_rows(y: torch.Tensor, bias: torch.Tensor) -> None:
 def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          a2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = 0,
          col_scale: Optional[torch.Tensor] = None, row_map: Optional[tuple[int, int, int]] = None,
-         norm: Optional[dict] = None, tag: str = "gemm") -> torch.Tensor:
+         norm: Optional[dict] = None, out2: Optional[torch.Tensor] = None, tag: str = "gemm") -> torch.Tensor:
     """out = epilogue(cat[a, a2] @ w.T).  a:(m,k1) bf16, a2:(m,k2) bf16 or None, w:(n,k1+k2) bf16, out bf16/fp32.
 
     norm = dict(cols=, seg=, w0=, w1=, eps=, rope_cols=, cos=, sin=, rows_per_pos=) enables the per-head
@@ -359,6 +359,12 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
         raise _lib.AmbError(f"gemm: unsupported output dtype {out.dtype}")
     g.c, g.ldc, g.c_fp32 = out.data_ptr(), out.stride(0), int(out.dtype == torch.float32)
     g.m, g.n, g.k = m, n, k
+    if out2 is not None:  # bf16 copy of the result (GEMM operand of a later linear)
+        _need(out2, torch.bfloat16, "out2")
+        assert out2.shape == out.shape and out2.stride(1) == 1
+        g.c2, g.ldc2 = out2.data_ptr(), out2.stride(0)
+    else:
+        g.c2, g.ldc2 = None, 0
     if bias is not None:
         _need(bias, torch.float32, "bias")
     g.bias = _ptr(bias)

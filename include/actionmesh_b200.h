@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 11
+#define AMB_ABI_VERSION 12
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -168,6 +168,11 @@ typedef struct amb_gemm_args {
   const float* rope_cos;
   const float* rope_sin;
   int32_t rope_rows_per_pos;
+  /* optional second output: the same final values rounded to bf16, (m', n) row-major with row stride ldc2 (plain epilogue only).
+   * Used with the fp32 residual stream: the fp32 result continues the stream, the bf16 copy is the GEMM operand of the
+   * long-skip linear (block.py:131-133), so no separate cast pass is needed. */
+  void* c2;
+  int64_t ldc2;
 } amb_gemm_args;
 
 int amb_gemm_bf16(const amb_gemm_args* args, amb_stream_t stream);
