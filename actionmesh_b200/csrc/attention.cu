@@ -10,7 +10,6 @@
 //               when the running max grew by more than 2^8), which is exact after the final 1/rowsum normalisation.
 // TMEM: S0 [0,64) S1 [64,128) O0 [128,128+D) O1 [128+D,128+2D)  -> 512 columns allocated.
 // The issue order  S0 S1 | PV0 S0' PV1 S1' | ...  keeps the tensor pipe busy with tile 1 while warpgroup 0 is in softmax.
-#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "ptx.cuh"
@@ -749,9 +748,8 @@ extern "C" int amb_flash_attn_fwd(const amb_attn_args* a, amb_stream_t stream) {
   if (a->head_dim == 64) return launch_attn_v1<64, 4>(a, s);
   // head_dim 128: the CTA-pair kernel for long key loops (its two softmax sets, three S buffers and the fix-up pass pay off
   // from a few dozen key tiles on: the inflated self-attention, 257 tiles); the single-CTA kernel for short ones (the
-  // per-frame cross-attention to 257 context tokens = 3 tiles).  AMB_ATTN_VER (development): 4 / 6 force one kernel.
-  static const int ver = []() { const char* e = getenv("AMB_ATTN_VER"); return e ? atoi(e) : 0; }();
+  // per-frame cross-attention to 257 context tokens = 3 tiles).
   const int key_tiles = (a->sk + 127) / 128;
-  if (ver == 4 || (ver == 0 && key_tiles < 48)) return launch_attn_v4(a, s);
+  if (key_tiles < 48) return launch_attn_v4(a, s);
   return launch_attn_pair(a, g_attn_trace, s);
 }

@@ -650,10 +650,8 @@ int launch_attn_pair(const amb_attn_args* a, long long* trace, cudaStream_t stre
   AttnParams p = make_attn_params(a, trace);
   dim3 grid(2 * ((a->sq + 255) / 256), a->heads, a->batch);  // cluster dims (2,1,1) are compiled in
   const long long units = (long long)(grid.x / 2) * grid.y * grid.z;
-  static const int mode = []() { const char* e = getenv("AMB_ATTN_MODE"); return e ? atoi(e) : 2; }();  // development switch: 0 = exact only
-  static const int emu = []() { const char* e = getenv("AMB_ATTN_EMU"); return e ? atoi(e) : 1; }();    // development switch
   auto exact = flash_attn_pair_kernel<KS, VS, 1, PA_EXACT>;
-  if (mode == 0 || units > PA_MAX_UNITS) {
+  if (units > PA_MAX_UNITS) {  // more units than fix-up flags: the exact organisation alone
     r = ensure_smem_optin(exact, L::TOTAL);
     if (r) return r;
     exact<<<grid, PA_THREADS, L::TOTAL, stream>>>(tmQ, tmK, tmV, p);
@@ -662,9 +660,7 @@ int launch_attn_pair(const amb_attn_args* a, long long* trace, cudaStream_t stre
   }
   p.dirty = pair_dirty_flags(stream);
   AMB_CHECK_ARG(p.dirty != nullptr, "flash_attn: could not allocate the fix-up flags");
-  auto fast = emu == 0 ? flash_attn_pair_kernel<KS, VS, 0, PA_FAST>
-            : emu == 2 ? flash_attn_pair_kernel<KS, VS, 2, PA_FAST>
-                       : flash_attn_pair_kernel<KS, VS, 1, PA_FAST>;
+  auto fast = flash_attn_pair_kernel<KS, VS, 1, PA_FAST>;  // one exponential pair in four on the FMA pipe (measured best of 0..2)
   auto fixup = flash_attn_pair_kernel<KS, VS, 1, PA_FIXUP>;
   r = ensure_smem_optin(fast, L::TOTAL);
   if (r) return r;

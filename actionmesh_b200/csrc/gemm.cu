@@ -667,8 +667,7 @@ extern "C" int amb_gemm_bf16(const amb_gemm_args* a, amb_stream_t stream) {
     AMB_CHECK_ARG(!a->residual && a->act == 0 && !a->col_scale && !a->c2, "gemm: head epilogue excludes residual/activation/col_scale/c2");
   }
   cudaStream_t s = (cudaStream_t)stream;
-  static const int two_cta = []() { const char* e = getenv("AMB_GEMM_2CTA"); return e ? atoi(e) : 1; }();  // 2-CTA kernel is the product path for N % 256 == 0
-  if (two_cta && a->n % 256 == 0 && a->m >= 256) return launch_gemm2<6>(a, s);
+  if (a->n % 256 == 0 && a->m >= 256) return launch_gemm2<6>(a, s);  // CTA pairs, 256 x 256 tiles
   if (a->n % 256 == 0) return launch_gemm<256, 4>(a, s);
   if (a->n % 128 == 0) return launch_gemm<128, 6>(a, s);
   return launch_gemm<64, 8>(a, s);

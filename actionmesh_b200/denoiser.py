@@ -344,7 +344,8 @@ class B200Denoiser:
     def _workspace(self, B: int, T: int, N: int, world: int = 1, slot: int = 0, shard=None) -> dict:
         """Activation buffers of one window shape.  `slot` > 0 gives additional independent sets of the same shape (the
         single-GPU emulation of several ranks in tests/test_window_shard_gpu.py); one shape stays resident."""
-        key = (B, T, N, world, slot)
+        symmetric = shard is not None and hasattr(shard, "empty_kv_local")   # the exchange decides where kv_local lives
+        key = (B, T, N, world, slot, id(shard) if symmetric else 0)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -370,7 +371,7 @@ class B200Denoiser:
             "pred": torch.empty(M, c.in_channels, dtype=bf, device=dev),
         }
         if world > 1:  # frame-sharded window: local [K|V] rows and the all-gathered buffer (one chunk per rank)
-            if shard is not None and hasattr(shard, "empty_kv_local"):
+            if symmetric:
                 ws["kv_local"] = shard.empty_kv_local(M, 2 * c.width, dev)     # symmetric memory mapped into every peer
             else:
                 ws["kv_local"] = torch.empty(M, 2 * c.width, dtype=bf, device=dev)

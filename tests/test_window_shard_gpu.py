@@ -59,8 +59,10 @@ def _worker(rank, world, port, q):
             if not res[-1]:
                 res[-1] = f"{kind.__name__} err {err}"
         q.put((rank, "ok" if all(r is True for r in res) else str(res)))
-    except Exception as e:  # noqa: BLE001
-        q.put((rank, repr(e)[:500]))
+    except Exception:  # noqa: BLE001
+        import traceback
+
+        q.put((rank, traceback.format_exc()[-1500:]))
     finally:
         dist.destroy_process_group()
 
