@@ -515,7 +515,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="temporal", choices=["temporal", "dp"])
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"],
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"],
                     help="per-layer K/V exchange of the sharded window: NCCL all-gather or copy-engine peer copies")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-video", action="store_true")

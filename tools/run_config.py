@@ -25,7 +25,7 @@ def main():
     ap.add_argument("config", choices=["c3", "c4", "c5"])
     ap.add_argument("--clips", type=int, default=16)
     ap.add_argument("--steps", type=int, default=None)
-    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peer"])
+    ap.add_argument("--exchange", default="peer", choices=["nccl", "peer"])
     args = ap.parse_args()
     rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
     torch.cuda.set_device(local)
