@@ -77,6 +77,19 @@ enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact 
 #define AMB_ATTN_TRACE 0  // 1: compile the clock64 role timeline (tools/attn_trace.py) into the kernels; off in the product build
 #endif
 
+#ifndef PA_ORDER
+#define PA_ORDER 0  // FAST tensor-pipe order per tile: 1 = P.V(j) keys 0-63, S(j+2), P.V(j) keys 64-127;  0 = S(j+2), P.V(j), P.V(j)
+#endif
+#ifndef PA_EMU
+#define PA_EMU 1  // FAST: quarters of the exponential pairs computed on the FMA pipe instead of the MUFU
+#endif
+#ifndef PA_LAYOUT
+#define PA_LAYOUT 1  // FAST softmax work split: 1 = every warp takes its 64-key half of EVERY tile (half the S->P latency per tile);
+#endif               //                          0 = two sets of 8 warps take whole tiles alternately
+#ifndef PA_ROLL_H
+#define PA_ROLL_H 0  // 1: the two key halves of a tile run through one rolled loop body (half the hot-loop code)
+#endif
+
 template <int KS, int VS, int EMU, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PA_THREADS, 1)
 flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -228,12 +241,21 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = 0; j < n_kv; ++j) {
         const bool tr = tracer && j >= 100 && j < 116;  // role 4 of the debug timeline
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 0] = clock64();
-        if (j + 2 < n_kv) {  // S_{j+2} first: the tensor pipe has it queued while the softmax warps work on S_j
-          mbar_wait(&k_full[ks], kph);
-          tc_fence_after();
-          issue_qk(buf2, ks);
-          if (++ks == KS) { ks = 0; kph ^= 1; }
-        }
+        const bool order1 = FAST && PA_ORDER == 1;
+        auto next_qk = [&]() {
+          if (j + 2 < n_kv) {
+            mbar_wait(&k_full[ks], kph);
+            tc_fence_after();
+            issue_qk(buf2, ks);
+            if (++ks == KS) { ks = 0; kph ^= 1; }
+          }
+        };
+        // order 0: S_{j+2} first, so the tensor pipe has it queued while the softmax warps work on S_j.
+        // order 1 (FAST): S_{j+2} goes BETWEEN the two halves of P_j·V_j.  The owning set needs as long for keys 64-127 as for
+        // keys 0-63, but half a P·V is only a quarter of a tile's tensor work: with S_{j+2} in between, three quarters of a
+        // tile are queued behind the first half of P_j before the second is due (ncu, r02 v7: the issuer sat 23 % of its time
+        // on p_half1 with order 0).
+        if (!order1) next_qk();
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 1] = clock64();
         mbar_wait(&v_full[vs], vph);
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 2] = clock64();
@@ -242,6 +264,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         tc_fence_after();
         if (FAST) {  // P·V of keys 0-63 starts while the owning set still works on keys 64-127
           issue_pv(buf, vs, j == 0, 0, 4, false);
+          if (order1) next_qk();
           mbar_wait(&p_half1[buf], bph);
           tc_fence_after();
           issue_pv(buf, vs, j == 0, 4, 8, true);
@@ -275,7 +298,8 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     float l_a = 0.f, l_b = 0.f;  // partial row sums: my 32 keys of every tile of my set
     bool dirty = false;
 
-    auto half_step = [&](int j, int buf, int h, bool masked) {
+    auto half_step_impl = [&](int j, int buf, int h, auto masked_c) {
+      constexpr bool masked = decltype(masked_c)::value;  // tail tiles get their own copy: no key masking in the hot one
       const bool tr = tracer && j >= 100 && j < 116;
       const uint32_t s_addr = tmem_base + buf * 128 + h * 64 + lane_sel;
       float s[32];  // s[4g + {0,1}] = row_a, keys 64 h + 8g + 2qd + {0,1};  s[4g + {2,3}] = row_a + 8, same keys
@@ -332,11 +356,65 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       }
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 3 + 2 * h] = clock64();
     };
+    auto half_step = [&](int j, int buf, int h, bool masked) {
+      if (masked) half_step_impl(j, buf, h, std::true_type{});
+      else half_step_impl(j, buf, h, std::false_type{});
+    };
 
+#if PA_LAYOUT == 1
+    // Key-half layout: `set` is the key half.  S_j -> P_j takes one half step (~1000 cycles) instead of two, which is what
+    // the three S/P buffers can cover: QK (512) + hand-offs (~700) + softmax + P.V (512) per buffer must fit 3 tile periods.
+    int buf = 0, jj = 0;
+    uint32_t bph = 0;
+    for (int j = 0; j < n_kv; ++j) {
+      const bool masked = has_tail && (jj == tiles_per_chunk - 1);
+      const bool tr = tracer && j >= 100 && j < 116;
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 0] = clock64();
+      mbar_wait(&s_full[buf], bph);
+      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 1] = clock64();
+      tc_fence_after();
+      if (j == 0) {
+        // every row's reference maximum is anchored on tile 0: my half's maximum, then the partner warp's through smem
+        float mx_a = -INFINITY, mx_b = -INFINITY;
+        {
+          float s[32];
+          tmem_ld16_256b_x8f(tmem_base + set * 64 + lane_sel, s);
+          tmem_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float a0 = s[4 * g], a1 = s[4 * g + 1], b0 = s[4 * g + 2], b1 = s[4 * g + 3];
+            if (masked) {
+              const int key = set * 64 + 8 * g + 2 * qd;
+              if (key >= last_valid) a0 = b0 = -INFINITY;
+              if (key + 1 >= last_valid) a1 = b1 = -INFINITY;
+            }
+            mx_a = fmaxf(mx_a, fmaxf(a0, a1));
+            mx_b = fmaxf(mx_b, fmaxf(b0, b1));
+          }
+        }
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+        float* x_mine = xch + 128 + set * 128;  // (the partial sums reuse these slots after the key loop)
+        const float* x_other = xch + 128 + (set ^ 1) * 128;
+        if (qd == 0) {
+          x_mine[row_a] = mx_a;
+          x_mine[row_a + 8] = mx_b;
+        }
+        named_bar_sync(MREF_BAR, 512);
+        m_a = fmaxf(mx_a, x_other[row_a]);
+        m_b = fmaxf(mx_b, x_other[row_a + 8]);
+      }
+      half_step(j, buf, set, masked);
+      if (++buf == PA_NBUF) { buf = 0; bph ^= 1; }
+      if (++jj == tiles_per_chunk) jj = 0;
+    }
+#else
+    int buf = set, jj = set % tiles_per_chunk;  // S/P buffer j % 3 (phase (j / 3) & 1) and tile-in-chunk j % tiles_per_chunk,
+    uint32_t bph = 0;                           // carried along instead of divided out every tile
     for (int j = set; j < n_kv; j += 2) {
-      const int buf = j % PA_NBUF;
-      const uint32_t bph = (j / PA_NBUF) & 1;
-      const bool masked = has_tail && (j % tiles_per_chunk == tiles_per_chunk - 1);
+      const bool masked = has_tail && (jj == tiles_per_chunk - 1);
       const bool tr = tracer && j >= 100 && j < 116;
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 0] = clock64();
       mbar_wait(&s_full[buf], bph);
@@ -379,9 +457,19 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         m_a = xch[row_a];
         m_b = xch[row_a + 8];
       }
+#if PA_ROLL_H
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) half_step(j, buf, h, masked);
+#else
       half_step(j, buf, 0, masked);
       half_step(j, buf, 1, masked);
+#endif
+      buf += 2;
+      if (buf >= PA_NBUF) { buf -= PA_NBUF; bph ^= 1; }
+      jj += 2;
+      while (jj >= tiles_per_chunk) jj -= tiles_per_chunk;
     }
+#endif
     if (__any_sync(0xffffffffu, dirty) && lane == 0) atomicOr(p.dirty + unit, 1);
 
     // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d); set s normalises columns [64 s, 64 s + 64) of its rows
@@ -660,7 +748,7 @@ int launch_attn_pair(const amb_attn_args* a, long long* trace, cudaStream_t stre
   }
   p.dirty = pair_dirty_flags(stream);
   AMB_CHECK_ARG(p.dirty != nullptr, "flash_attn: could not allocate the fix-up flags");
-  auto fast = flash_attn_pair_kernel<KS, VS, 1, PA_FAST>;  // one exponential pair in four on the FMA pipe (measured best of 0..2)
+  auto fast = flash_attn_pair_kernel<KS, VS, PA_EMU, PA_FAST>;  // one exponential pair in four on the FMA pipe (measured best of 0..2)
   auto fixup = flash_attn_pair_kernel<KS, VS, 1, PA_FIXUP>;
   r = ensure_smem_optin(fast, L::TOTAL);
   if (r) return r;

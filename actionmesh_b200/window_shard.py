@@ -117,6 +117,21 @@ class PeerFrameShard(FrameShard):
         self._uses = {}
         self.stream = None
 
+    @staticmethod
+    def available(device) -> bool:
+        """Collective probe: can every rank allocate symmetric memory on its device?  (All ranks get the same answer, so a
+        caller may choose the NCCL exchange instead without the ranks diverging.)"""
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            symm_mem.empty((1024,), dtype=torch.bfloat16, device=device)
+        except Exception:  # noqa: BLE001 - any allocator / driver refusal means "not available"
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        return bool(flag.item())
+
     def empty_kv_local(self, rows: int, cols: int, device) -> torch.Tensor:
         """(2, rows, cols) bf16 symmetric buffer; index [parity] is what the K/V projection of an exchange writes."""
         import torch.distributed._symmetric_memory as symm_mem

@@ -222,6 +222,8 @@ def run_b200(args):
         configure_nccl_env()  # NCCL protocol / channel defaults for the sharded window's K/V all-gather (before init)
         dist.init_process_group("nccl", device_id=dev)
         if T_WIN % world == 0:
+            if args.exchange == "peer" and not PeerFrameShard.available(dev):
+                args.exchange = "nccl"  # no symmetric memory on this box: the NCCL all-gather is the other exchange
             shard = PeerFrameShard() if args.exchange == "peer" else FrameShard()
     K, W = args.steps, max(args.warmup, 0)
     T, N, C, S, Dc = T_WIN, N_TOK, C_LAT, S_CTX, D_CTX

@@ -331,6 +331,10 @@ GROUPS = {
     "gemm_perf": group_gemm_perf, "attn_perf": group_attn_perf,
 }
 TAG = os.environ.get("AMB_PROBE_TAG", "")
+if os.environ.get("AMB_PROBE_LIB"):  # bring-up only: probe an experimental build (tools/build_variant.sh) instead of the product library
+    from actionmesh_b200 import _lib as _amb_lib
+
+    _amb_lib.LIB_PATH = os.path.abspath(os.environ["AMB_PROBE_LIB"])
 
 
 def run_group(name):
