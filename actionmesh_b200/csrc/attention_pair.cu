@@ -29,17 +29,21 @@
 //   17   MMA issuer (leader CTA only) + TMEM owner
 //
 // Two softmax organisations share everything else (MODE template parameter):
-//   FAST  (the one that runs): the 16 softmax warps form two SETS that take alternate key tiles (set 0 even, set 1 odd), so
-//         while one set sits in the latency phases of its tile (S visible, TMEM load, P store + hand-over) the other set
-//         keeps the MUFU / FMA pipes busy: ncu of the single-set version showed all warps in the same phase at the same
-//         time (53 % of a warp's time in the exponentials, competing; 47 % in latencies, all idle together —
-//         profiles/r02_ncu_attn_pair_v6b_summary.txt).  A warp owns 16 rows and ALL 128 keys of its tiles, processed as
-//         two 64-key halves handed to the tensor pipe separately (P·V of keys 0-63 overlaps the exponentials of 64-127).
-//         Both sets accumulate into the one O and use the row reference maxima fixed by set 0 on tile 0; there is NO
-//         in-loop rescale: a row whose probabilities leave the safe range marks its (batch, head, 256-row) unit dirty ...
-//   EXACT ... and the exact kernel (the single-set organisation described above, with the in-loop slow path) is launched
+//   FAST  (the one that runs): same warp -> (rows, key half) map, but NO in-loop maximum exchange and NO rescale: the row
+//         reference maxima are fixed on tile 0 (one 512-thread named barrier, once), every warp then turns its 64-key half
+//         of EVERY tile into P with no communication at all, and S_j -> P_j takes one half step (~1000 cycles).  That
+//         latency is what three S/P buffers can cover: QK (512) + hand-offs (~700) + softmax + P·V (512) per buffer must
+//         fit three tile periods; the earlier organisation (two sets of 8 warps taking whole tiles alternately, two half
+//         steps per tile) was latency-bound at ~1290 cycles per tile against a tensor floor of 1024
+//         (profiles/r02_attn_pair_v8_ab_and_timeline.log).  A row whose probabilities leave the safe range marks its
+//         (batch, head, 256-row) unit dirty ...
+//   EXACT ... and the exact kernel (per-tile agreement of the two warps of a row group, in-loop slow path) is launched
 //         right behind the fast one: it returns at once for clean units and recomputes dirty ones.  Results are exact either
 //         way; with q/k RMS-normalised as in this model the fix-up essentially never has work.
+//
+// Issuer: two barrier polls per tile instead of four: `v_full[i]` carries V_i AND K_{i+2} (the producer loads what one
+// iteration consumes onto one barrier), `p_ready` collects both key halves of P_i.  The tensor pipe's queue is shallow, so
+// every poll of the issuer is tensor idle time: with four polls per tile the issuer sat ~25 % of its time in them (ncu).
 #include <mutex>
 #include <type_traits>
 #include "common.cuh"
@@ -63,13 +67,13 @@ struct PairSmem {
   static constexpr int XCH_OFF = V_OFF + VS * KV_BYTES;      // float[3][128 rows]: row maxima / partial sums exchanged between warps
   static constexpr int FLAG_OFF = XCH_OFF + 3 * 128 * 4;      // int[8 row groups][2 tile parities]: slow-path requests
   static constexpr int BAR_OFF = FLAG_OFF + 8 * 2 * 4;
-  static constexpr int NUM_BARS = 1 + 2 * KS + 2 * VS + 4 * PA_NBUF;
+  static constexpr int NUM_BARS = 1 + 2 * KS + 2 * VS + 3 * PA_NBUF;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
 
-// which exponential pairs run on the FMA pipe: EMU = quarters of all pairs (0..3); (g, r) = (column group, row A/B)
+// which exponential pairs run on the FMA pipe: EMU = quarters of all pairs (0..3; 4 = one eighth); (g, r) = (column group, row A/B)
 __host__ __device__ constexpr bool pa_emulated(int emu, int g, int r) {
-  return emu == 0 ? false : emu == 1 ? (r == 0 && (g & 1) == 0) : emu == 2 ? (((g + r) & 1) == 0) : !(r == 1 && (g & 1) == 1);
+  return emu == 0 ? false : emu == 4 ? (r == 0 && (g & 3) == 0) : emu == 1 ? (r == 0 && (g & 1) == 0) : emu == 2 ? (((g + r) & 1) == 0) : !(r == 1 && (g & 1) == 1);
 }
 
 enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact on dirty units only / two-set fast path
@@ -77,17 +81,8 @@ enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact 
 #define AMB_ATTN_TRACE 0  // 1: compile the clock64 role timeline (tools/attn_trace.py) into the kernels; off in the product build
 #endif
 
-#ifndef PA_ORDER
-#define PA_ORDER 0  // FAST tensor-pipe order per tile: 1 = P.V(j) keys 0-63, S(j+2), P.V(j) keys 64-127;  0 = S(j+2), P.V(j), P.V(j)
-#endif
 #ifndef PA_EMU
-#define PA_EMU 1  // FAST: quarters of the exponential pairs computed on the FMA pipe instead of the MUFU
-#endif
-#ifndef PA_LAYOUT
-#define PA_LAYOUT 1  // FAST softmax work split: 1 = every warp takes its 64-key half of EVERY tile (half the S->P latency per tile);
-#endif               //                          0 = two sets of 8 warps take whole tiles alternately
-#ifndef PA_ROLL_H
-#define PA_ROLL_H 0  // 1: the two key halves of a tile run through one rolled loop body (half the hot-loop code)
+#define PA_EMU 1  // FAST: quarters of the exponential pairs computed on the FMA pipe instead of the MUFU (measured best of 0, 1/8, 1, 2)
 #endif
 
 template <int KS, int VS, int EMU, int MODE>
@@ -105,14 +100,13 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   float* xch = reinterpret_cast<float*>(smem + L::XCH_OFF);
   volatile int* flags = reinterpret_cast<volatile int*>(smem + L::FLAG_OFF);
   uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);  // leader's copy is live
-  uint64_t* k_full = q_full + 1;          // [KS] leader
+  uint64_t* k_full = q_full + 1;          // [KS] leader: K_0 and K_1 only (the prologue's tiles)
   uint64_t* k_empty = k_full + KS;        // [KS] both (multicast commit)
-  uint64_t* v_full = k_empty + KS;        // [VS] leader
+  uint64_t* v_full = k_empty + KS;        // [VS] leader: what iteration i consumes, V_i and K_{i+2}
   uint64_t* v_empty = v_full + VS;        // [VS] both
   uint64_t* s_full = v_empty + VS;        // [3]  both: S_j complete in this CTA's TMEM
-  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: P_j written.  EXACT: 32 warp arrivals (16 per CTA).  FAST: keys 0-63
-  uint64_t* p_half1 = p_ready + PA_NBUF;  // [3]  of P_j (8 warps of the owning set per CTA = 16 arrivals); keys 64-127 here
-  uint64_t* pv_done = p_half1 + PA_NBUF;  // [3]  both: P_j·V_j (and everything before it) complete
+  uint64_t* p_ready = s_full + PA_NBUF;   // [3]  leader: P_j written: 32 warp arrivals (16 per CTA)
+  uint64_t* pv_done = p_ready + PA_NBUF;  // [3]  both: P_j·V_j (and everything before it) complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + PA_NBUF);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -138,8 +132,7 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int s = 0; s < VS; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
       for (int b = 0; b < PA_NBUF; ++b) {
         mbar_init(&s_full[b], 1);
-        mbar_init(&p_ready[b], FAST ? 16 : 32);
-        mbar_init(&p_half1[b], 16);
+        mbar_init(&p_ready[b], 32);
         mbar_init(&pv_done[b], 1);
       }
       fence_mbar_init();
@@ -163,31 +156,41 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncwarp();
     int ks = 0, vs = 0;
     uint32_t kph = 0, vph = 0;
-    int chunk = 0, jj = 0;
-    for (int j = 0; j < n_kv; ++j) {
-      const int key0 = jj * PA_BK;
-      mbar_wait(&k_empty[ks], kph ^ 1);
+    int chunk_k = 0, jj_k = 0, chunk_v = 0, jj_v = 0;  // (chunk, tile in chunk) of the next K tile / V tile
+    auto load_k = [&](uint64_t* bar) {  // keys [key0 + 64 rank, +64): two 64-column boxes of 8 KB
       if (elect_one()) {
-        if (leader) mbar_expect_tx(&k_full[ks], 2 * L::KV_BYTES);
-        uint8_t* sk = smem + L::K_OFF + ks * L::KV_BYTES;  // keys [key0 + 64 rank, +64): two 64-column boxes of 8 KB
-        tma_load_5d_pair(sk, &tmK, &k_full[ks], 0, key0 + 64 * (int)rank, head, batch, chunk, kEvictLast);
-        tma_load_5d_pair(sk + 8192, &tmK, &k_full[ks], 64, key0 + 64 * (int)rank, head, batch, chunk, kEvictLast);
+        uint8_t* sk = smem + L::K_OFF + ks * L::KV_BYTES;
+        const int key0 = jj_k * PA_BK + 64 * (int)rank;
+        tma_load_5d_pair(sk, &tmK, bar, 0, key0, head, batch, chunk_k, kEvictLast);
+        tma_load_5d_pair(sk + 8192, &tmK, bar, 64, key0, head, batch, chunk_k, kEvictLast);
       }
       __syncwarp();
       if (++ks == KS) { ks = 0; kph ^= 1; }
+      if (++jj_k == tiles_per_chunk) { jj_k = 0; ++chunk_k; }
+    };
+    for (int t = 0; t < 2 && t < n_kv; ++t) {  // K_0, K_1 on their own barriers (fresh stages: nothing to wait for)
+      if (leader && elect_one()) mbar_expect_tx(&k_full[t], 2 * L::KV_BYTES);
+      __syncwarp();
+      load_k(&k_full[t]);
+    }
+    for (int i = 0; i < n_kv; ++i) {  // iteration i of the issuer consumes V_i and K_{i+2}: one barrier for both
+      const bool has_k = i + 2 < n_kv;
       mbar_wait(&v_empty[vs], vph ^ 1);
+      if (has_k) mbar_wait(&k_empty[ks], kph ^ 1);
       if (elect_one()) {
-        if (leader) mbar_expect_tx(&v_full[vs], 2 * L::KV_BYTES);
+        if (leader) mbar_expect_tx(&v_full[vs], (has_k ? 4 : 2) * L::KV_BYTES);
         uint8_t* sv = smem + L::V_OFF + vs * L::KV_BYTES;  // 128 keys x d-columns [64 rank, +64): one box of 16 KB
-        tma_load_5d_pair(sv, &tmV, &v_full[vs], 64 * (int)rank, key0, head, batch, chunk, kEvictLast);
+        tma_load_5d_pair(sv, &tmV, &v_full[vs], 64 * (int)rank, jj_v * PA_BK, head, batch, chunk_v, kEvictLast);
       }
       __syncwarp();
+      if (has_k) load_k(&v_full[vs]);
       if (++vs == VS) { vs = 0; vph ^= 1; }
-      if (++jj == tiles_per_chunk) { jj = 0; ++chunk; }
+      if (++jj_v == tiles_per_chunk) { jj_v = 0; ++chunk_v; }
     }
   } else if (warp == 17) {
     if (leader) {
-      // ===================== MMA issuer (leader CTA; one elected lane inside a converged warp) =====================
+      // ===================== MMA issuer (leader CTA; one elected lane inside a converged warp, so that descriptors and
+      // addresses stay in uniform registers: a divergent single-thread loop pays R2UR moves per MMA, ~90 cycles each) =========
       constexpr uint32_t idesc_qk = make_idesc_bf16(256, PA_BK, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc_bf16(256, 128, 0, 1);
       const uint32_t sq_addr = smem_u32(smem + L::Q_OFF);
@@ -209,31 +212,29 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int buf, int vstage, bool first, int k0, int k1, bool last) {
+      auto issue_pv = [&](int buf, int vstage, bool first) {
         const uint64_t vd = make_desc_mnmajor_sw128(sv_addr + vstage * L::KV_BYTES, 16384);
         const uint32_t pa = tmem_base + buf * 128;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = k0; kk < k1; ++kk)  // 128 keys in 16-key steps: 8 packed P columns (key half h = kk / 4 keeps its P in
+          for (int kk = 0; kk < 8; ++kk)  // 128 keys in 16-key steps: 8 packed P columns (key half h = kk / 4 keeps its P in
                                           // the first 32 of its own 64 S columns), 16 V rows (2 KB) per step
             mma_ts_pair(o_tmem, pa + (kk >> 2) * 64 + (kk & 3) * 8, vd + 128 * kk, idesc_pv, (!first || kk != 0) ? 1u : 0u);
-          if (last) {
-            tc_commit_pair(&v_empty[vstage]);
-            tc_commit_pair(&pv_done[buf]);
-          }
+          tc_commit_pair(&v_empty[vstage]);
+          tc_commit_pair(&pv_done[buf]);
         }
         __syncwarp();
       };
 
       mbar_wait(q_full, 0);
       int ks = 0, vs = 0;
-      uint32_t kph = 0, vph = 0;
+      uint32_t vph = 0;
       const int npro = n_kv < 2 ? n_kv : 2;
       for (int j = 0; j < npro; ++j) {
-        mbar_wait(&k_full[ks], kph);
+        mbar_wait(&k_full[j], 0);
         tc_fence_after();
         issue_qk(j, ks);
-        if (++ks == KS) { ks = 0; kph ^= 1; }
+        if (++ks == KS) ks = 0;
       }
       int buf = 0, buf2 = 2 % PA_NBUF;  // buffer of tile j / of tile j + 2
       uint32_t bph = 0;
@@ -241,42 +242,25 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       for (int j = 0; j < n_kv; ++j) {
         const bool tr = tracer && j >= 100 && j < 116;  // role 4 of the debug timeline
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 0] = clock64();
-        const bool order1 = FAST && PA_ORDER == 1;
-        auto next_qk = [&]() {
-          if (j + 2 < n_kv) {
-            mbar_wait(&k_full[ks], kph);
-            tc_fence_after();
-            issue_qk(buf2, ks);
-            if (++ks == KS) { ks = 0; kph ^= 1; }
-          }
-        };
-        // order 0: S_{j+2} first, so the tensor pipe has it queued while the softmax warps work on S_j.
-        // order 1 (FAST): S_{j+2} goes BETWEEN the two halves of P_j·V_j.  The owning set needs as long for keys 64-127 as for
-        // keys 0-63, but half a P·V is only a quarter of a tile's tensor work: with S_{j+2} in between, three quarters of a
-        // tile are queued behind the first half of P_j before the second is due (ncu, r02 v7: the issuer sat 23 % of its time
-        // on p_half1 with order 0).
-        if (!order1) next_qk();
+        mbar_wait(&v_full[vs], vph);  // V_j and K_{j+2}
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 1] = clock64();
-        mbar_wait(&v_full[vs], vph);
+        tc_fence_after();
+        if (j + 2 < n_kv) {  // S_{j+2} first: the tensor pipe has it queued while the softmax warps work on S_j
+          issue_qk(buf2, ks);
+          if (++ks == KS) ks = 0;
+        }
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 2] = clock64();
         mbar_wait(&p_ready[buf], bph);
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 3] = clock64();
         tc_fence_after();
-        if (FAST) {  // P·V of keys 0-63 starts while the owning set still works on keys 64-127
-          issue_pv(buf, vs, j == 0, 0, 4, false);
-          if (order1) next_qk();
-          mbar_wait(&p_half1[buf], bph);
-          tc_fence_after();
-          issue_pv(buf, vs, j == 0, 4, 8, true);
-        } else {
-          issue_pv(buf, vs, j == 0, 0, 8, true);
-        }
+        issue_pv(buf, vs, j == 0);
         if (tr) p.trace[(4 * 16 + (j - 100)) * 8 + 4] = clock64();
         if (++vs == VS) { vs = 0; vph ^= 1; }
         if (++buf == PA_NBUF) { buf = 0; bph ^= 1; }
         if (++buf2 == PA_NBUF) buf2 = 0;
       }
     }
+    __syncwarp();
   } else {
     if constexpr (FAST) {
     // ===================== softmax, FAST: warp = (set, lane quarter, 16-row half); set s takes tiles j = s, s+2, ... ============
@@ -350,9 +334,8 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        uint64_t* bar = h ? &p_half1[buf] : &p_ready[buf];
-        if (leader) mbar_arrive(bar);
-        else mbar_arrive_remote(bar, 0);
+        if (leader) mbar_arrive(&p_ready[buf]);
+        else mbar_arrive_remote(&p_ready[buf], 0);
       }
       if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 3 + 2 * h] = clock64();
     };
@@ -361,7 +344,6 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       else half_step_impl(j, buf, h, std::false_type{});
     };
 
-#if PA_LAYOUT == 1
     // Key-half layout: `set` is the key half.  S_j -> P_j takes one half step (~1000 cycles) instead of two, which is what
     // the three S/P buffers can cover: QK (512) + hand-offs (~700) + softmax + P.V (512) per buffer must fit 3 tile periods.
     int buf = 0, jj = 0;
@@ -410,66 +392,6 @@ flash_attn_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       if (++buf == PA_NBUF) { buf = 0; bph ^= 1; }
       if (++jj == tiles_per_chunk) jj = 0;
     }
-#else
-    int buf = set, jj = set % tiles_per_chunk;  // S/P buffer j % 3 (phase (j / 3) & 1) and tile-in-chunk j % tiles_per_chunk,
-    uint32_t bph = 0;                           // carried along instead of divided out every tile
-    for (int j = set; j < n_kv; j += 2) {
-      const bool masked = has_tail && (jj == tiles_per_chunk - 1);
-      const bool tr = tracer && j >= 100 && j < 116;
-      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 0] = clock64();
-      mbar_wait(&s_full[buf], bph);
-      if (tr) p.trace[(set * 16 + (j - 100)) * 8 + 1] = clock64();
-      tc_fence_after();
-      if (j == 0) {
-        // set 0 anchors every row's reference maximum on tile 0 and publishes it to set 1
-        float mx_a = -INFINITY, mx_b = -INFINITY;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          float s[32];
-          tmem_ld16_256b_x8f(tmem_base + h * 64 + lane_sel, s);
-          tmem_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float a0 = s[4 * g], a1 = s[4 * g + 1], b0 = s[4 * g + 2], b1 = s[4 * g + 3];
-            if (masked) {
-              const int key = h * 64 + 8 * g + 2 * qd;
-              if (key >= last_valid) a0 = b0 = -INFINITY;
-              if (key + 1 >= last_valid) a1 = b1 = -INFINITY;
-            }
-            mx_a = fmaxf(mx_a, fmaxf(a0, a1));
-            mx_b = fmaxf(mx_b, fmaxf(b0, b1));
-          }
-        }
-        mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
-        mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
-        m_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
-        m_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
-        if (n_kv > 1) {
-          if (qd == 0) {
-            xch[row_a] = m_a;
-            xch[row_a + 8] = m_b;
-          }
-          __syncwarp();
-          named_bar_arrive(MREF_BAR, 512);
-        }
-      } else if (j == 1) {
-        named_bar_sync(MREF_BAR, 512);
-        m_a = xch[row_a];
-        m_b = xch[row_a + 8];
-      }
-#if PA_ROLL_H
-#pragma unroll 1
-      for (int h = 0; h < 2; ++h) half_step(j, buf, h, masked);
-#else
-      half_step(j, buf, 0, masked);
-      half_step(j, buf, 1, masked);
-#endif
-      buf += 2;
-      if (buf >= PA_NBUF) { buf -= PA_NBUF; bph ^= 1; }
-      jj += 2;
-      while (jj >= tiles_per_chunk) jj -= tiles_per_chunk;
-    }
-#endif
     if (__any_sync(0xffffffffu, dirty) && lane == 0) atomicOr(p.dirty + unit, 1);
 
     // ---- epilogue: O / rowsum -> bf16 -> global (b, s, h, d); set s normalises columns [64 s, 64 s + 64) of its rows
