@@ -5,8 +5,15 @@ Mirrors actionmesh/model/image_encoder.py:16-55: constructor kwargs `pretrained_
 The transformer (HF `Dinov2Model`, transformers/models/dinov2/modeling_dinov2.py: patch-embed conv, CLS + interpolated
 position embeddings, 24 x [LN, MHA(16 heads, d_h 64), LayerScale, LN, MLP GELU, LayerScale], final LN) runs on the sm_100a
 kernels: patchify (im2col) -> tcgen05 GEMM, LayerNorm, fused-QKV tcgen05 GEMM, tcgen05 flash attention (head_dim 64),
-GEMM epilogues with bias / GELU / LayerScale / fp32 residual.  The residual stream is kept in fp32 (the reference runs
-DinoV2 in fp32, outside autocast, pipeline.py:664-667); GEMM operands are bf16 with fp32 accumulation.
+GEMM epilogues with bias / GELU / LayerScale / fp32 residual.
+
+Precision.  The reference runs DinoV2 in fp32, outside autocast (pipeline.py:664-667), so the default here is fp32-grade
+(`precision="fp32"`): every linear runs on the tensor cores with three-way split bf16 operands (x = hi + lo; activations
+[hi|lo|hi], weights [hi|hi|lo] along K, fp32 accumulation: all products but lo·lo, relative error ~2^-16 — the machinery of
+the Stage-II query path), activations and the residual stream stay fp32 between kernels, and the 257-token attention runs in
+fp32 on the CUDA cores (csrc/attention_small.cu).  The encoder is 2.5 TFLOP per clip against 16 400 for the denoise, so
+3x its GEMM work is invisible.  `precision="bf16"` keeps the round-1 path (bf16 operands, tcgen05 flash attention at
+head_dim 64; last_hidden_state within 1e-2 of fp32).
 
 Image preprocessing (HF BitImageProcessor in the reference: bicubic resize to 256, centre crop 224, 1/255 rescale, ImageNet
 mean/std) runs on the GPU with the semantics of the reference's pinned transformers<5 / Pillow path, bit-exact on the uint8
@@ -42,11 +49,14 @@ class B200ImageEncoder:
     def __init__(self, pretrained_dino_feature_extractor: Optional[str] = None,
                  pretrained_dino_model: Optional[str] = None, *, hidden_size: int = 1024, num_layers: int = 24,
                  num_heads: int = 16, patch_size: int = 14, image_size: int = 224, mlp_ratio: int = 4,
-                 layer_norm_eps: float = 1e-6):
+                 layer_norm_eps: float = 1e-6, precision: str = "fp32"):
         self.hidden_size, self.num_layers, self.num_heads = hidden_size, num_layers, num_heads
         self.patch_size, self.image_size, self.mlp_ratio, self.eps = patch_size, image_size, mlp_ratio, layer_norm_eps
         if hidden_size // num_heads != 64 or hidden_size % 256:
             raise AmbError("B200ImageEncoder: head_dim must be 64 and hidden_size a multiple of 256")
+        if precision not in ("fp32", "bf16"):
+            raise AmbError("B200ImageEncoder: precision must be 'fp32' (reference-grade, default) or 'bf16'")
+        self.precision = precision
         self._device = torch.device("cpu")
         self._w: dict = {}
         self._loaded = False
@@ -103,7 +113,11 @@ class B200ImageEncoder:
         sd = {k[len("dinov2."):] if k.startswith("dinov2.") else k: v for k, v in sd.items()}
         D, P = self.hidden_size, self.patch_size
         f32 = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
-        W = lambda t: t.to(torch.bfloat16).contiguous()
+        if self.precision == "fp32":   # split operand [hi | hi | lo] along K (ops.split3, weight layout)
+            W = lambda t: ops.split3(t.contiguous(), torch.empty(t.shape[0], 3 * t.shape[1], dtype=torch.bfloat16, device=dev),
+                                     weight=True)
+        else:
+            W = lambda t: t.to(torch.bfloat16).contiguous()
         w = {}
         kreal = 3 * P * P
         self.kpad = (kreal + 63) // 64 * 64
@@ -193,6 +207,8 @@ class B200ImageEncoder:
         F_ = D * self.mlp_ratio
         bf = torch.bfloat16
         x = w["base"].repeat(T, 1)                      # (M, D) fp32 residual stream: cls+pos rows (device copy)
+        if self.precision == "fp32":
+            return self._encode_fp32(px, x, T, L, M, F_)
         patches = ops.patchify(px, P, self.kpad)
         ops.gemm(patches, w["patch.w"], x, bias=w["patch.b"], residual=x, row_map=(g * g, L, 1))
         xn = torch.empty(M, D, dtype=bf, device=dev)
@@ -213,5 +229,41 @@ class B200ImageEncoder:
             ops.gemm(xn, w[p + "fc1.w"], hid, bias=w[p + "fc1.b"], act=1)
             ops.gemm(hid, w[p + "fc2.w"], x, bias=w[p + "fc2.b"], col_scale=w[p + "ls2"], residual=x)
         out = torch.empty(M, D, dtype=torch.float32, device=dev)
+        ops.layernorm(x, w["ln.g"], w["ln.b"], self.eps, out=out)
+        return out.view(T, L, D)
+
+    def _encode_fp32(self, px: torch.Tensor, x: torch.Tensor, T: int, L: int, M: int, F_: int) -> torch.Tensor:
+        """The fp32-grade path: split-bf16 tensor-core GEMMs, fp32 activations, fp32 CUDA-core attention."""
+        w, dev = self._w, self._device
+        D, H, P = self.hidden_size, self.num_heads, self.patch_size
+        g = self.image_size // P
+        bf, f32 = torch.bfloat16, torch.float32
+        # im2col of the stride-P patch convolution: a pure re-indexing of the fp32 pixels (columns ordered (c, py, px) like the
+        # conv weight), zero-padded to the GEMM's K granularity
+        cols = torch.zeros(T * g * g, self.kpad, dtype=f32, device=dev)
+        cols[:, :3 * P * P] = px.reshape(T, 3, g, P, g, P).permute(0, 2, 4, 1, 3, 5).reshape(T * g * g, 3 * P * P)
+        p3 = ops.split3(cols, torch.empty(T * g * g, 3 * self.kpad, dtype=bf, device=dev))
+        ops.gemm(p3, w["patch.w"], x, bias=w["patch.b"], residual=x, row_map=(g * g, L, 1))
+        t32 = torch.empty(M, D, dtype=f32, device=dev)
+        a3 = torch.empty(M, 3 * D, dtype=bf, device=dev)
+        qkv = torch.empty(M, 3 * D, dtype=f32, device=dev)
+        att = torch.empty(M, D, dtype=f32, device=dev)
+        hid = torch.empty(M, F_, dtype=f32, device=dev)
+        h3 = torch.empty(M, 3 * F_, dtype=bf, device=dev)
+        scale = 1.0 / math.sqrt(D // H)
+        for i in range(self.num_layers):
+            p = f"encoder.layer.{i}."
+            ops.layernorm(x, w[p + "n1.g"], w[p + "n1.b"], self.eps, out=t32)
+            ops.split3(t32, a3)
+            ops.gemm(a3, w[p + "qkv.w"], qkv, bias=w[p + "qkv.b"])
+            ops.attn_small_f32(qkv, T, L, H, scale, att, tag="attn_dino")
+            ops.split3(att, a3)
+            ops.gemm(a3, w[p + "o.w"], x, bias=w[p + "o.b"], col_scale=w[p + "ls1"], residual=x)
+            ops.layernorm(x, w[p + "n2.g"], w[p + "n2.b"], self.eps, out=t32)
+            ops.split3(t32, a3)
+            ops.gemm(a3, w[p + "fc1.w"], hid, bias=w[p + "fc1.b"], act=1)
+            ops.split3(hid, h3)
+            ops.gemm(h3, w[p + "fc2.w"], x, bias=w[p + "fc2.b"], col_scale=w[p + "ls2"], residual=x)
+        out = torch.empty(M, D, dtype=f32, device=dev)
         ops.layernorm(x, w["ln.g"], w["ln.b"], self.eps, out=out)
         return out.view(T, L, D)

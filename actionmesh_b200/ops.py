@@ -402,6 +402,25 @@ def gemm(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, *, bias: Optional[
     return out
 
 
+def attn_small_f32(qkv: torch.Tensor, frames: int, seq: int, heads: int, scale: float, out: torch.Tensor,
+                   tag: str = "attn_small") -> torch.Tensor:
+    """fp32 attention of `frames` independent sequences of `seq` <= 320 tokens, head_dim 64 (DinoV2).
+    qkv: fp32 (frames * seq, 3 * heads * 64) = [q | k | v] of a fused projection; out: fp32 (frames * seq, heads * 64)."""
+    global launch_count
+    _need(qkv, torch.float32, "qkv")
+    _need(out, torch.float32, "out")
+    D = heads * 64
+    assert qkv.dim() == 2 and out.dim() == 2 and qkv.stride(1) == 1 and out.stride(1) == 1
+    assert qkv.shape == (frames * seq, 3 * D) and out.shape == (frames * seq, D)
+    base = qkv.data_ptr()
+    with _Timed(tag, (frames, heads, seq, seq, 64)):
+        rc = _lib.load_library().amb_attn_small_f32(base, base + 4 * D, base + 8 * D, qkv.stride(0), frames, seq, heads,
+                                                    float(scale), out.data_ptr(), out.stride(0), _stream())
+    _lib.check(rc, "amb_attn_small_f32")
+    launch_count += 1
+    return out
+
+
 def flash_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, scale: float, *,
                kv_chunks: int = 1, tag: str = "attn") -> torch.Tensor:
     """softmax(scale q kᵀ) v, non-causal.  q:(B,Sq,H,D) k,v:(B,Sk,H,D) out:(B,Sq,H,D) — arbitrary (16-byte aligned)

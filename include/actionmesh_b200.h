@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define AMB_ABI_VERSION 12
+#define AMB_ABI_VERSION 13
 
 typedef void* amb_stream_t; /* cudaStream_t */
 
@@ -202,6 +202,13 @@ typedef struct amb_attn_args {
 } amb_attn_args;
 
 int amb_flash_attn_fwd(const amb_attn_args* args, amb_stream_t stream);
+
+/* fp32 attention for short sequences, head_dim 64 (the DinoV2 encoder, which the reference runs in fp32 outside autocast:
+ * actionmesh/pipeline.py:664-667, model/image_encoder.py:38-55 -> HF Dinov2SelfAttention's scaled_dot_product_attention).
+ * q, k, v: fp32, element (frame f, token s, head h, d) at ptr[(f * seq + s) * ld + h * 64 + d]; out likewise with ldo.
+ * seq <= 320.  No mask, non-causal; softmax(scale * q k^T) v with fp32 arithmetic throughout (CUDA cores). */
+int amb_attn_small_f32(const float* q, const float* k, const float* v, int64_t ld, int frames, int seq, int heads, float scale,
+                       float* out, int64_t ldo, amb_stream_t stream);
 
 /* Debug only: device buffer (5 roles x 16 iterations x 8 events of int64 clock64 stamps) receiving the role timeline of
  * CTA (0,0,0) of the head_dim-128 attention kernel; NULL switches tracing off (the default). */
