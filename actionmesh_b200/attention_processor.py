@@ -26,9 +26,18 @@ class B200AttentionProcessor:
     def __init__(self):
         self._cache = {}
 
+    def invalidate(self) -> None:
+        """Drop every packed-weight entry (e.g. after swapping parameter tensors of the modules this processor serves)."""
+        self._cache.clear()
+
     def _packed(self, attn):
-        key = (attn.to_q.weight.data_ptr(), attn.to_k.weight.data_ptr(), attn.to_v.weight.data_ptr(), attn.to_q.weight.device)
-        hit = self._cache.get("k")
+        # one entry per module (a processor instance may be shared by all layers); the key carries the pointers AND the
+        # in-place version counters of every weight that is packed, so load_state_dict / copy_ re-packs
+        params = [attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight]
+        params += [t for t in (getattr(attn.norm_q, "weight", None), getattr(attn.norm_k, "weight", None), attn.to_out[0].bias)
+                   if t is not None]
+        key = tuple((t.data_ptr(), t._version, t.device) for t in params)
+        hit = self._cache.get(id(attn))
         if hit is not None and hit[0] == key:
             return hit[1]
         for name in ("to_q", "to_k", "to_v"):
@@ -50,7 +59,7 @@ class B200AttentionProcessor:
         w["eps"] = float(getattr(attn.norm_q, "eps", 1e-6))
         w["o.w"] = f32(attn.to_out[0].weight).to(torch.bfloat16).contiguous()
         w["o.b"] = f32(attn.to_out[0].bias).contiguous() if attn.to_out[0].bias is not None else None
-        self._cache["k"] = (key, w)
+        self._cache[id(attn)] = (key, w)
         return w
 
     @torch.no_grad()
