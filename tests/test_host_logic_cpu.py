@@ -103,3 +103,32 @@ def test_exp2_emulation_polynomial_error_bound():
     e = (p.view(np.uint32) + (t.view(np.uint32) << np.uint32(23))).view(np.float32)
     rel = (e.astype(np.float64) - 2.0 ** x.astype(np.float64)) / 2.0 ** x.astype(np.float64)
     assert np.abs(rel).max() < 1e-4 and abs(rel.mean()) < 1e-5, (np.abs(rel).max(), rel.mean())
+
+
+def test_gelu_erfc_form_error_bound():
+    """The GEMM epilogue evaluates the reference's exact (erf) GELU as x * Phi(x) with Phi(-|x|) = erfc(|x| / sqrt 2) / 2 through
+    Abramowitz-Stegun 7.1.26 (csrc/gemm.cu gelu_erf).  Re-evaluate that form in fp32 with the constants parsed from the source:
+    the absolute error against erf-GELU in float64 stays below 1e-6 over |x| <= 12 — the same as the fp32 erf formula."""
+    import math
+    import re
+
+    import numpy as np
+
+    src = open(os.path.join(ROOT, "actionmesh_b200", "csrc", "gemm.cu")).read()
+    body = src[src.index("__device__ __forceinline__ float gelu_erf"):]
+    body = body[:body.index("\n}\n")]
+    consts = [np.float32(v) for v in re.findall(r"(-?[01]\.\d{9})f", body)]
+    assert len(consts) == 5, consts                       # a5 .. a1 of 7.1.26 in Horner order
+    assert "0.3275911f" in body
+    f = np.float32
+    x = np.linspace(-12.0, 12.0, 2_000_001).astype(np.float32)
+    ax = np.abs(x)
+    t = (f(1.0) / (f(0.3275911 * 0.70710678118654752440) * ax + f(1.0))).astype(np.float32)
+    p = (t * consts[0] + consts[1]).astype(np.float32)
+    for c in consts[2:]:
+        p = (p * t + c).astype(np.float32)
+    e = np.exp2((ax * ax * f(-0.5 * 1.4426950408889634)).astype(np.float32)).astype(np.float32)
+    q = (f(0.5) * (p * t).astype(np.float32) * e).astype(np.float32)
+    g = (x * np.where(x >= 0, f(1.0) - q, q)).astype(np.float32)
+    ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x[::200].astype(np.float64)])
+    assert np.abs(g[::200].astype(np.float64) - ref).max() < 1e-6
