@@ -76,7 +76,7 @@ __host__ __device__ constexpr bool pa_emulated(int emu, int g, int r) {
   return emu == 0 ? false : emu == 4 ? (r == 0 && (g & 3) == 0) : emu == 1 ? (r == 0 && (g & 1) == 0) : emu == 2 ? (((g + r) & 1) == 0) : !(r == 1 && (g & 1) == 1);
 }
 
-enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact on dirty units only / two-set fast path
+enum : int { PA_EXACT = 0, PA_FIXUP = 1, PA_FAST = 2 };  // MODE: exact / exact on dirty units only / fast path (fixed reference maxima)
 #ifndef AMB_ATTN_TRACE
 #define AMB_ATTN_TRACE 0  // 1: compile the clock64 role timeline (tools/attn_trace.py) into the kernels; off in the product build
 #endif
