@@ -445,8 +445,11 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 // add.  x is clamped at -126.
 __device__ __forceinline__ void exp2_poly2(float x0, float x1, float& e0, float& e1) {
   const float kMagic = 12582912.0f;  // 1.5 * 2^23
-  x0 = fmaxf(x0, -126.0f);
-  x1 = fmaxf(x1, -126.0f);
+  // clamp BOTH ways: below, 2^x underflows to the smallest normal instead of wrapping the exponent field; above, an argument
+  // past 127 would wrap into the sign bit and come back as a tiny NEGATIVE number — invisible to the row-sum range check of
+  // the fixed-reference attention pass.  Clamped to 127 it yields 2^127, which that check catches (the unit is redone exactly).
+  x0 = fminf(fmaxf(x0, -126.0f), 127.0f);
+  x1 = fminf(fmaxf(x1, -126.0f), 127.0f);
   const uint64_t x = pk2(x0, x1);
   const uint64_t t = add2(x, pk2(kMagic, kMagic));
   const uint64_t n = add2(t, pk2(-kMagic, -kMagic));

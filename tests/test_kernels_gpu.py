@@ -99,6 +99,13 @@ def test_gemm_is_linear_in_a(probe):
     ("d64_s257", (3, 4, 257, 257, 64), {}),
     ("d64_fused", (2, 16, 257, 257, 64), dict(fused=True)),
     ("window_t2", (2, 16, 2 * 2049, 2 * 2049, 128), dict(fused=True)),
+    # >= 48 key tiles: the CTA-pair kernel.  Logits with std 8 push most rows out of the fixed-reference safe range, so the
+    # units are marked dirty by the fast pass and recomputed by the exact pass launched behind it (ragged q and key tails)
+    ("pair_dirty_units_fixup", (1, 2, 300, 128 * 50 + 17, 128), dict(mode="sharp8")),
+    ("pair_clean_ragged", (2, 2, 300, 128 * 50 + 17, 128), {}),
+    # one key far above the row reference, in a key slot whose exp2 is the FMA-pipe polynomial: must be caught (argument clamp
+    # at 127 -> 2^127 -> row-sum range check) and the unit redone exactly; the output is then v of that key
+    ("pair_single_spike_key", (1, 2, 300, 128 * 50, 128), dict(mode="spike")),
 ])
 def test_flash_attention(probe, name, args, kw):
     res = {}
@@ -112,7 +119,19 @@ def test_flash_attention_late_rescale(probe):
     from actionmesh_b200 import ops
 
     g = torch.Generator().manual_seed(5)
-    B, S, H, D = 1, 128 * 9 + 17, 2, 128
+    _late_rescale_case(probe, 128 * 9 + 17)
+
+
+def test_flash_attention_late_rescale_pair_kernel(probe):
+    """The same construction over 50 key tiles: the CTA-pair kernel, every unit dirty, exact pass with in-loop rescales."""
+    _late_rescale_case(probe, 128 * 50 + 17)
+
+
+def _late_rescale_case(probe, S):
+    from actionmesh_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    B, H, D = 1, 2, 128
     q = torch.randn(B, S, H, D, generator=g)
     k = torch.randn(B, S, H, D, generator=g) * 0.05
     v = torch.randn(B, S, H, D, generator=g)

@@ -250,6 +250,14 @@ def _attn_case(res, name, B, H, Sq, Sk, D, *, mode="rand", fused=False, timing=F
         k = torch.zeros_like(k)
     elif mode == "sharp":
         q = q * 4
+    elif mode == "spike":  # ONE key (tile 10, column 3: a slot whose exponential runs on the FMA pipe for half of the rows) scores
+        u = torch.zeros(D, device=dev)  # 75-225 nats above everything else: exp2 arguments far past 127 in the fast pass
+        u[0] = 1.0
+        q = (q.float() + 4.0 * u).bfloat16()
+        k = k.clone()
+        k[:, 128 * 10 + 3] = (424.0 * u).bfloat16()
+    elif mode == "sharp8":  # logits with std 8: most rows leave the fixed-reference safe range after the first key tile
+        q = q * 8
     out = torch.full((B, Sq, H, D), 3.0, device=dev, dtype=torch.bfloat16)
     if kv_chunks > 1:
         kc = k.view(B, kv_chunks, Sk // kv_chunks, H, D)
