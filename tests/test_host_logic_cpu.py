@@ -132,3 +132,22 @@ def test_gelu_erfc_form_error_bound():
     g = (x * np.where(x >= 0, f(1.0) - q, q)).astype(np.float32)
     ref = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x[::200].astype(np.float64)])
     assert np.abs(g[::200].astype(np.float64) - ref).max() < 1e-6
+
+
+def test_image_encoder_constructor_contract():
+    """B200ImageEncoder keeps the reference's constructor keywords (image_encoder.py:16-36) and refuses what it cannot honour
+    at construction time: a hub id / missing directory (no network, no silent default) and an unknown precision."""
+    import pytest
+
+    from actionmesh_b200._lib import AmbError
+    from actionmesh_b200.image_encoder import B200ImageEncoder
+
+    enc = B200ImageEncoder(pretrained_dino_feature_extractor=None, pretrained_dino_model=None)
+    assert enc.precision == "fp32" and enc.image_preprocess_dino is not None
+    assert B200ImageEncoder(precision="bf16").precision == "bf16"
+    with pytest.raises(AmbError):
+        B200ImageEncoder(pretrained_dino_model="facebook/dinov2-large")
+    with pytest.raises(AmbError):
+        B200ImageEncoder(precision="fp16")
+    with pytest.raises(AmbError):
+        enc.to("cpu")
